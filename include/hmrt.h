@@ -1,0 +1,196 @@
+/*
+ * hmrt.h -- C ABI of the B200-native heightfield ray traversal + point rasterisation path.
+ *
+ * This is the drop-in boundary.  Every entry point names the
+ * reference interface it replaces; paths are relative to the reference tree
+ * (GPUHeightmapRaytracer/src/...).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value when the CUDA
+ *     runtime failed, or a negative HMRT_E_* code for argument errors.  Nothing exits the
+ *     process (the reference's checkCudaErrors logs and continues, inc/helper_cuda.h:985-995).
+ *   - "d_" pointers are device pointers on the context's device, "h_" pointers are host
+ *     pointers.  Device pointers are BORROWED exactly as in the reference: the caller
+ *     allocates, fills and frees them (main.cpp:1012-1013, :623-624, :1022-1023).
+ *   - a context is bound to one device and one stream and is not re-entrant (the reference
+ *     calls its three entry points from one thread only, main.cpp:947-966,1079).
+ *   - pyramid layout = the reference's: `levels` square grids, coarsest level at float
+ *     offset 0, finest level last; level i has resolution coarse_res * 2^(levels-1-i) and
+ *     starts at idx[i] = idx[i+1] + res[i+1]^2 (main.cpp:995-1003, CudaKernel.cu:250-258).
+ *   - framebuffer = packed RGB8, row-major, pixel (px,py) at (px + py*W)*3, py = 0 is the
+ *     first row written (GL bottom row in the reference, CudaKernel.cu:202,219-221).
+ */
+#ifndef HMRT_H_
+#define HMRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMRT_VERSION 100
+#define HMRT_MAX_LEVELS 16
+
+/* argument errors (negative so they never collide with cudaError_t) */
+#define HMRT_E_ARG (-1)      /* null / out-of-range argument */
+#define HMRT_E_STATE (-2)    /* call order: e.g. trace before set_heightmap */
+#define HMRT_E_SHAPE (-3)    /* grid does not tile / too large for 32-bit cell indices */
+#define HMRT_E_NOMEM (-4)    /* host allocation failed */
+
+typedef struct hmrt_ctx hmrt_ctx;
+
+/* == struct CudaSpace::Color (CudaKernel.cuh:37-48): 3 bytes, no padding. */
+typedef struct hmrt_color {
+  uint8_t r, g, b;
+} hmrt_color;
+
+/* The per-frame arguments of CudaSpace::rayTrace (CudaKernel.cuh:49, call site main.cpp:686). */
+typedef struct hmrt_camera {
+  float frame_dim[3]; /* frame_dimensions: image-plane width, height, distance (main.cpp:57) */
+  float forward[3];   /* camera_forward: unit length, not parallel to +y (CudaKernel.cu:237) */
+  float position[3];  /* grid_camera_position, finest-cell units (main.cpp:514-517) */
+} hmrt_camera;
+
+/*
+ * Optional per-pixel traversal record (parity instrumentation; the reference has no such
+ * output -- it is what castRay leaves in its by-reference `ray_position`, CudaKernel.cu:121).
+ * x,y,z: ray position when castRay returned, in castRay's MIRRORED space (CudaKernel.cu:130-150).
+ * flags: HMRT_HIT_* bits | (loop iterations, primary + shadow segments) << HMRT_HIT_STEPS_SHIFT.
+ */
+typedef struct hmrt_hit {
+  float x, y, z;
+  uint32_t flags;
+} hmrt_hit;
+#define HMRT_HIT_HIT 1u       /* castRay returned from the finest level (CudaKernel.cu:161-167) */
+#define HMRT_HIT_MIRROR_X 2u  /* ray_direction.x was negative (CudaKernel.cu:130-135) */
+#define HMRT_HIT_MIRROR_Z 4u  /* ray_direction.z was negative (CudaKernel.cu:141-146) */
+#define HMRT_HIT_SHADOWED 8u  /* shadow segment hit the terrain (extension, see hmrt_trace_opts) */
+#define HMRT_HIT_STEPS_SHIFT 8
+
+/*
+ * Options of a trace call.  Zero-initialise, then set what you need; hmrt_trace_opts_default()
+ * fills the reference's behaviour (no shadows, whole frame).
+ */
+typedef struct hmrt_trace_opts {
+  int use_color_map; /* rayTrace's `use_color` (CudaKernel.cu:163-166) */
+  float max_height;  /* rayTrace's `max_height` (CudaKernel.cu:41,153) */
+  /* Shadow rays (north star; the reference has none, semantics defined in DESIGN.md section 5):
+   * from the primary hit point, stepped back by shadow_bias along the primary ray, a second
+   * castRay toward light_dir; if it hits, every colour channel is halved (c >> 1). */
+  int shadows;
+  float light_dir[3]; /* unit vector TOWARD the light */
+  float shadow_bias;  /* cells; 0 selects the default 1/16 */
+  /* Row-tile sharding (multi-GPU): the frame is cut into tiles of
+   * HMRT_ROW_TILE rows; this call renders tiles tile_first, tile_first + tile_stride, ...
+   * and stores local tile j at rows [j*HMRT_ROW_TILE, ...) of the output.  first=0, stride=1
+   * (or stride 0) = whole frame in natural order. */
+  int tile_first;
+  int tile_stride;
+} hmrt_trace_opts;
+#define HMRT_ROW_TILE 8
+
+/* LAS public-header fields the rasteriser needs (liblas::Header accessors used at
+ * main.cpp:137-164,187-202): X = raw*scale + offset in double (libLAS 1.8.0 Point::GetX). */
+typedef struct hmrt_las_transform {
+  double scale[3];
+  double offset[3];
+  double min[3];        /* header.GetMinX/Y/Z (main.cpp:200-202) */
+  float cell_size[3];   /* cell_size (main.cpp:154-155: 2.0 in the reference) */
+  float origin[2];      /* section origin in cell units (main.cpp:174, :205-206) */
+} hmrt_las_transform;
+
+/* ---- context ---------------------------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device` (replaces cudaGLSetGLDevice(gpuGetMaxGflopsDeviceId()),
+ * main.cpp:1008).  Creates no stream: work runs on the stream set by hmrt_set_stream
+ * (default: the legacy default stream, like the reference). */
+int hmrt_create(int device, hmrt_ctx** out);
+int hmrt_destroy(hmrt_ctx* ctx);
+/* `cuda_stream` is a cudaStream_t passed as void* (0 = default stream). */
+int hmrt_set_stream(hmrt_ctx* ctx, void* cuda_stream);
+/* Block until all work queued by this context has finished (the reference synchronises inside
+ * every call, CudaKernel.cu:301,307,316,325; here calls are asynchronous unless stated). */
+int hmrt_synchronize(hmrt_ctx* ctx);
+const char* hmrt_error_string(int code);
+int hmrt_version(void);
+
+/* ---- pyramid layout (main.cpp:995-1003 == CudaKernel.cu:250-258) ----------------------- */
+
+/* Fills res[i], idx[i] for i in [0,levels) (level 0 = finest) and the total float count
+ * (= stride_x * coarse_res^2).  Any output pointer may be NULL. */
+int hmrt_pyramid_layout(int coarse_res, int levels, int* res, int64_t* idx, int64_t* total);
+
+/* ---- ray traversal ---------------------------------------------------------------------- */
+
+/* == CudaSpace::initializeDeviceVariables (CudaKernel.cuh:50, CudaKernel.cu:313-317,245-272).
+ * d_pyramid / d_color_map are borrowed; d_color_map may be NULL when use_color_map is never
+ * set.  The reference also takes texture_res and stride_x; the resolution is a per-call
+ * argument here and stride_x is implied by (coarse_res, levels). */
+int hmrt_set_heightmap(hmrt_ctx* ctx, const float* d_pyramid, const hmrt_color* d_color_map,
+                       int coarse_res, int levels, float max_height);
+
+void hmrt_trace_opts_default(hmrt_trace_opts* opts, float max_height);
+
+/* == CudaSpace::rayTrace (CudaKernel.cuh:49, CudaKernel.cu:291-308) + cuda_setParameters
+ * (CudaKernel.cu:227-240) + cuda_rayTrace (CudaKernel.cu:195-222) for n_frames cameras in ONE
+ * launch.  Frame f is written at d_rgb + f * rows_local * W * 3 (rows_local = rows selected by
+ * the tile options; = H for a whole frame).  d_hits (optional, same indexing, one record per
+ * pixel) selects the instrumented kernel.  Asynchronous on the context's stream. */
+int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
+               const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits);
+
+/* Same call with HOST output: renders into a context-owned device framebuffer and copies the
+ * result to h_rgb (pinned memory recommended); synchronous, like the reference's rayTrace +
+ * the GL read-back it feeds (main.cpp:675-703). */
+int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
+                    const hmrt_trace_opts* opts, uint8_t* h_rgb);
+
+/* Number of local rows selected by (H, tile_first, tile_stride). */
+int hmrt_rows_local(int H, int tile_first, int tile_stride);
+
+/* == CudaSpace::freeDeviceVariables (CudaKernel.cuh:51): forget the borrowed pointers. */
+int hmrt_clear_heightmap(hmrt_ctx* ctx);
+
+/* ---- point rasterisation (loadLASToSection inner loop, main.cpp:193-234) ---------------- */
+
+/* Zero a pyramid (the reference's `new float[n]()`, main.cpp:259) and, if given, the colour
+ * keys / colour map (`new Color[n]` default-constructs to 0,0,0, main.cpp:260). */
+int hmrt_clear_section(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int levels,
+                       uint64_t* d_color_keys, hmrt_color* d_color_map);
+
+/* Bin LAS point records into the FINEST level of d_pyramid with an order-independent
+ * float-as-int atomic max (heights are >= +0, main.cpp:227-233 + :259).
+ *   d_records  n records of record_len bytes each, LAS 1.2 point data formats 0-3
+ *   point_format  0..3 (selects where classification / RGB live)
+ *   first_index  global index of record 0 (file order), used for the colour keys
+ *   d_color_keys  optional, res0^2 uint64: keeps (index+1)<<24 | rgb of the LAST point in file
+ *                 order per cell (the reference's last-writer-wins, main.cpp:223-224)
+ * Points outside [0,res0)^2 or with classification 7 are skipped (main.cpp:209). */
+int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len,
+                     int point_format, const hmrt_las_transform* xf, int64_t first_index,
+                     float* d_pyramid, int coarse_res, int levels, uint64_t* d_color_keys);
+
+/* Same for PointdataGenerator output (PointdataGenerator/main.cpp:186-205): n float32
+ * (x, y, z) triples, treated as LAS coordinates with scale 1 and offset 0. */
+int hmrt_scatter_xyz(hmrt_ctx* ctx, const float* d_xyz, int64_t n, const hmrt_las_transform* xf,
+                     float* d_pyramid, int coarse_res, int levels);
+
+/* Build every coarser level from the finest one: level i+1 = max of its 2x2 children
+ * (the fixed point of main.cpp:227-233). */
+int hmrt_build_mips(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int levels);
+
+/* Turn colour keys into the reference's colour map (cells never written stay 0,0,0). */
+int hmrt_resolve_colors(hmrt_ctx* ctx, const uint64_t* d_color_keys, hmrt_color* d_color_map,
+                        int64_t n_cells);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t hmrt_launch_count(const hmrt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMRT_H_ */

@@ -1,0 +1,47 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY.
+# Builds oracle/_ref/libhmrt_ref.so (+ libhmrt_ref_dpow.so): the reference's OWN device code
+# (GPUHeightmapRaytracer/src/CudaKernel.cu lines 1-286, i.e. everything before the <<<>>> host
+# wrappers) compiled for the host by plain g++ from where it lies under /root/reference.
+# Nothing from the reference is written into the repository: the two mechanical shims below
+# live in a mktemp directory that is removed on exit; only the .so files land in oracle/_ref/
+# (git-ignored, shipped to the GPU box with the snapshot).
+#
+#   shim 1: `head -n 286` + closing brace  -> drops the host wrappers g++ cannot parse (<<<>>>)
+#   shim 2: sed on a temp copy of CudaKernel.cuh:43-45 -> the MSVC-only functional cast
+#           `unsigned char (expr)` becomes `(unsigned char)(expr)` (never executed on this path)
+#   oracle/shim/: device_launch_parameters.h (thread-local blockIdx/threadIdx, fp32 pow
+#           overload = original MSVC meaning) and an empty math_functions.hpp.
+#
+# No FMA contraction (x86-64 baseline has no FMA; -ffp-contract=off makes that explicit).
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ref="${HMRT_REFERENCE_ROOT:-/root/reference}/GPUHeightmapRaytracer"
+out="$here/_ref"
+cuda_inc="${CUDA_HOME:-/usr/local/cuda}/include"
+
+if [ ! -f "$ref/src/CudaKernel.cu" ]; then
+  echo "build_ref.sh: reference tree not present at $ref (expected on the GPU box): keeping prebuilt $out" >&2
+  exit 0
+fi
+
+mkdir -p "$out"
+tmp="$(mktemp -d)"
+trap 'rm -rf "$tmp"' EXIT
+
+sed -e 's/unsigned char (glm::floor/(unsigned char)(glm::floor/' "$ref/src/CudaKernel.cuh" > "$tmp/CudaKernel.cuh"
+{ head -n 286 "$ref/src/CudaKernel.cu"; echo "}"; } > "$tmp/ref_device.cpp"
+
+cxxflags=(-std=c++14 -O2 -fPIC -ffp-contract=off -w
+          -I"$here/shim" -I"$tmp" -I"$ref/inc" -I"$cuda_inc" -I"$here")
+
+build_variant() {  # $1 = output name, $2... = extra defines
+  local name="$1"; shift
+  g++ "${cxxflags[@]}" "$@" -c "$tmp/ref_device.cpp" -o "$tmp/ref_device_$name.o"
+  g++ "${cxxflags[@]}" "$@" -c "$here/ref_harness.cpp" -o "$tmp/ref_harness_$name.o"
+  g++ -shared -o "$out/$name.so" "$tmp/ref_device_$name.o" "$tmp/ref_harness_$name.o" -lpthread
+}
+
+build_variant libhmrt_ref -DHMRT_REF_FLOAT_MATH   # canonical: pow(float,int) in fp32 (MSVC/CUDA 8)
+build_variant libhmrt_ref_dpow                   # variant: g++/nvcc-Linux promotion to double
+echo "built $out/libhmrt_ref.so $out/libhmrt_ref_dpow.so"

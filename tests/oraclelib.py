@@ -1,0 +1,181 @@
+"""Test-side access to the CPU checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+`oracle()`  -> oracle/_build/libhmrt_oracle.so  (plain-C restatement, hmrt_oracle.c)
+`ref()`     -> oracle/_ref/libhmrt_ref.so       (the reference's own code, host-compiled)
+`ref_dpow()`-> oracle/_ref/libhmrt_ref_dpow.so  (same, Linux double-pow/floor meaning)
+Nothing here is imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "gpu-heightmap-raytracer_b200"))
+
+from hmrt._abi import Camera, Color, Hit, LasTransform, TraceOpts  # noqa: E402  (struct layouts only)
+
+ORACLE_SO = REPO / "oracle" / "_build" / "libhmrt_oracle.so"
+REF_SO = REPO / "oracle" / "_ref" / "libhmrt_ref.so"
+REF_DPOW_SO = REPO / "oracle" / "_ref" / "libhmrt_ref_dpow.so"
+
+_P = C.c_void_p
+_TRACE_ARGS = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(TraceOpts),
+               C.c_int, C.c_int, C.c_int, _P, _P]
+_cache = {}
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-s", "-C", str(REPO / "oracle"), "_build/libhmrt_oracle.so"], check=True)
+
+
+def oracle() -> C.CDLL:
+    if "oracle" not in _cache:
+        if not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < (REPO / "oracle" / "hmrt_oracle.c").stat().st_mtime:
+            build_oracle()
+        lib = C.CDLL(str(ORACLE_SO))
+        lib.hmrt_oracle_trace.restype = C.c_int
+        lib.hmrt_oracle_trace.argtypes = _TRACE_ARGS
+        lib.hmrt_oracle_pyramid_layout.restype = C.c_int
+        lib.hmrt_oracle_pyramid_layout.argtypes = [C.c_int, C.c_int, _P, _P, _P]
+        lib.hmrt_oracle_rasterise_las.restype = C.c_int
+        lib.hmrt_oracle_rasterise_las.argtypes = [_P, C.c_int64, C.c_int, C.c_int, C.POINTER(LasTransform), _P, C.c_int, C.c_int, _P]
+        lib.hmrt_oracle_rasterise_xyz.restype = C.c_int
+        lib.hmrt_oracle_rasterise_xyz.argtypes = [_P, C.c_int64, C.POINTER(LasTransform), _P, C.c_int, C.c_int]
+        lib.hmrt_oracle_build_mips.restype = C.c_int
+        lib.hmrt_oracle_build_mips.argtypes = [_P, C.c_int, C.c_int]
+        lib.hmrt_oracle_pdg_generate.restype = C.c_int
+        lib.hmrt_oracle_pdg_generate.argtypes = [C.c_int, C.c_uint64, _P]
+        _cache["oracle"] = lib
+    return _cache["oracle"]
+
+
+def _load_ref(path: Path, key: str):
+    if key not in _cache:
+        if not path.exists():
+            if (Path("/root/reference") / "GPUHeightmapRaytracer").exists():
+                subprocess.run(["bash", str(REPO / "oracle" / "build_ref.sh")], check=True)
+        if not path.exists():
+            _cache[key] = None
+        else:
+            lib = C.CDLL(str(path))
+            lib.hmrt_ref_trace.restype = C.c_int
+            lib.hmrt_ref_trace.argtypes = _TRACE_ARGS
+            lib.hmrt_ref_float_math.restype = C.c_int
+            _cache[key] = lib
+    return _cache[key]
+
+
+def ref():
+    return _load_ref(REF_SO, "ref")
+
+
+def ref_dpow():
+    return _load_ref(REF_DPOW_SO, "ref_dpow")
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy helpers (host logic of the tests; not an implementation of the traced path)
+
+def pyramid_layout(coarse_res: int, levels: int):
+    """res[i], idx[i], total -- main.cpp:995-1003."""
+    res = [0] * levels
+    idx = [0] * levels
+    res[levels - 1] = coarse_res
+    for i in range(levels - 2, -1, -1):
+        idx[i] = idx[i + 1] + res[i + 1] * res[i + 1]
+        res[i] = res[i + 1] * 2
+    return res, idx, idx[0] + res[0] * res[0]
+
+
+def pyramid_from_finest(finest: np.ndarray, levels: int) -> np.ndarray:
+    """Max-pyramid in the reference layout (coarsest first) from a [R0,R0] float32 grid
+    indexed [z, x]; 'level i+1 = max of 2x2 children' (fixed point of main.cpp:227-233)."""
+    r0 = finest.shape[0]
+    assert finest.shape == (r0, r0) and r0 % (1 << (levels - 1)) == 0
+    coarse = r0 >> (levels - 1)
+    res, idx, total = pyramid_layout(coarse, levels)
+    out = np.zeros(total, dtype=np.float32)
+    cur = np.ascontiguousarray(finest, dtype=np.float32)
+    out[idx[0]:idx[0] + r0 * r0] = cur.ravel()
+    for l in range(1, levels):
+        r = res[l]
+        cur = cur.reshape(r, 2, r, 2).max(axis=(1, 3))
+        out[idx[l]:idx[l] + r * r] = cur.ravel()
+    return out
+
+
+def sines_terrain(r0: int, seed: int = 0) -> np.ndarray:
+    """Analytic terrain of SURVEY.md Appendix A (computed in float64, rounded once) + a seeded
+    small-scale perturbation so neighbouring cells differ.  [z, x] float32, >= 0."""
+    x = np.arange(r0, dtype=np.float64)[None, :]
+    z = np.arange(r0, dtype=np.float64)[:, None]
+    h = 40 + 25 * np.sin(0.013 * x) * np.cos(0.017 * z) + 10 * np.sin(0.11 * x + 0.07 * z) + 3 * np.sin(0.9 * x) * np.sin(0.8 * z)
+    rng = np.random.default_rng(seed)
+    h = h + rng.random((r0, r0)) * 0.5
+    return np.maximum(h, 0).astype(np.float32)
+
+
+def make_camera(position, forward, frame_dim=(32.0, 18.0, 20.0)) -> Camera:
+    f = np.asarray(forward, dtype=np.float64)
+    f = (f / np.linalg.norm(f)).astype(np.float32)
+    cam = Camera()
+    cam.frame_dim[:] = [float(v) for v in frame_dim]
+    cam.forward[:] = [float(v) for v in f]
+    cam.position[:] = [float(np.float32(v)) for v in position]
+    return cam
+
+
+def make_opts(max_height: float, use_color_map=False, shadows=False, light_dir=(0.3, 0.8, 0.52), shadow_bias=0.0,
+              tile_first=0, tile_stride=1) -> TraceOpts:
+    o = TraceOpts()
+    o.use_color_map = int(use_color_map)
+    o.max_height = float(np.float32(max_height))
+    o.shadows = int(shadows)
+    l = np.asarray(light_dir, dtype=np.float64)
+    l = (l / np.linalg.norm(l)).astype(np.float32)
+    o.light_dir[:] = [float(v) for v in l]
+    o.shadow_bias = float(shadow_bias)
+    o.tile_first = tile_first
+    o.tile_stride = tile_stride
+    return o
+
+
+def cpu_trace(lib_fn, pyramid: np.ndarray, color_map, coarse_res: int, levels: int, W: int, H: int, cam: Camera,
+              opts: TraceOpts, n_threads: int | None = None, rows=None, want_hits=True):
+    """Run hmrt_oracle_trace / hmrt_ref_trace.  Returns (rgb[H,W,3] u8, hits structured array or None)."""
+    n_threads = n_threads or os.cpu_count() or 1
+    rgb = np.zeros((H, W, 3), dtype=np.uint8)
+    hits = np.zeros((H, W), dtype=hit_dtype) if want_hits else None
+    r0, r1 = rows if rows is not None else (0, H)
+    cm_ptr = color_map.ctypes.data if color_map is not None else None
+    rc = lib_fn(pyramid.ctypes.data, cm_ptr, coarse_res, levels, W, H, C.byref(cam), C.byref(opts), n_threads, r0, r1,
+                rgb.ctypes.data, hits.ctypes.data if hits is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"cpu trace failed: {rc}")
+    return rgb, hits
+
+
+hit_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("flags", "<u4")])
+assert hit_dtype.itemsize == C.sizeof(Hit)
+
+
+def hit_cells(hits: np.ndarray, r0: int):
+    """Un-mirrored finest hit cell per pixel (-1 = miss), and hit mask; SURVEY.md section 8(a) R4."""
+    flags = hits["flags"]
+    hit = (flags & 1) != 0
+    cx = np.floor(hits["x"]).astype(np.int64)
+    cz = np.floor(hits["z"]).astype(np.int64)
+    cx = np.where((flags & 2) != 0, r0 - 1 - cx, cx)
+    cz = np.where((flags & 4) != 0, r0 - 1 - cz, cz)
+    cell = np.where(hit, cx + cz * r0, -1)
+    return cell, hit
+
+
+def steps_of(hits: np.ndarray) -> np.ndarray:
+    return hits["flags"] >> 8
