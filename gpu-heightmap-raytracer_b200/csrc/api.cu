@@ -1,0 +1,151 @@
+/*
+ * api.cu -- context management and the small host-side pieces of the C ABI (include/hmrt.h).
+ * Reference counterparts: initializeDeviceVariables / freeDeviceVariables
+ * (GPUHeightmapRaytracer/src/CudaKernel.cu:313-326, :245-286) and the pyramid tables
+ * (main.cpp:995-1003).
+ */
+#include <new>
+#include <stdio.h>
+#include <string.h>
+
+#include "hmrt_internal.cuh"
+
+namespace hmrt {
+
+/* main.cpp:995-1003 == CudaKernel.cu:250-258 */
+int pyramid_layout(int coarse_res, int levels, int* res, int64_t* idx, int64_t* total) {
+  if (coarse_res < 1 || levels < 1 || levels > HMRT_MAX_LEVELS) return HMRT_E_ARG;
+  int r[HMRT_MAX_LEVELS];
+  int64_t ix[HMRT_MAX_LEVELS];
+  r[levels - 1] = coarse_res;
+  ix[levels - 1] = 0;
+  for (int i = levels - 2; i >= 0; i--) {
+    ix[i] = ix[i + 1] + (int64_t)r[i + 1] * r[i + 1];
+    if (r[i + 1] > (1 << 29)) return HMRT_E_SHAPE;
+    r[i] = r[i + 1] * 2;
+  }
+  const int64_t n = ix[0] + (int64_t)r[0] * r[0];
+  /* cell indices are 32-bit in the kernels, coordinates must be exact in fp32 */
+  if (n >= ((int64_t)1 << 32) || r[0] > (1 << 23)) return HMRT_E_SHAPE;
+  for (int i = 0; i < levels; i++) {
+    if (res) res[i] = r[i];
+    if (idx) idx[i] = ix[i];
+  }
+  if (total) *total = n;
+  return 0;
+}
+
+}  // namespace hmrt
+
+extern "C" {
+
+int hmrt_version(void) { return HMRT_VERSION; }
+
+const char* hmrt_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case HMRT_E_ARG: return "invalid argument";
+    case HMRT_E_STATE: return "invalid call order (no heightmap set)";
+    case HMRT_E_SHAPE: return "unsupported grid shape";
+    case HMRT_E_NOMEM: return "host allocation failed";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+int hmrt_create(int device, hmrt_ctx** out) {
+  if (!out) return HMRT_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  HMRT_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(device);
+  HMRT_CUDA(cudaFree(0)); /* create the primary context now so later errors are attributable */
+  hmrt_ctx* c = new (std::nothrow) hmrt_ctx();
+  if (!c) return HMRT_E_NOMEM;
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) {
+    delete c;
+    return (int)e;
+  }
+  *out = c;
+  return 0;
+}
+
+int hmrt_destroy(hmrt_ctx* ctx) {
+  if (!ctx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_frames) cudaFree(ctx->d_frames);
+  if (ctx->d_fb) cudaFree(ctx->d_fb);
+  delete ctx;
+  return (int)e;
+}
+
+int hmrt_set_stream(hmrt_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return HMRT_E_ARG;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int hmrt_synchronize(hmrt_ctx* ctx) {
+  if (!ctx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  HMRT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hmrt_pyramid_layout(int coarse_res, int levels, int* res, int64_t* idx, int64_t* total) {
+  return hmrt::pyramid_layout(coarse_res, levels, res, idx, total);
+}
+
+int hmrt_set_heightmap(hmrt_ctx* ctx, const float* d_pyramid, const hmrt_color* d_color_map, int coarse_res,
+                       int levels, float max_height) {
+  if (!ctx || !d_pyramid) return HMRT_E_ARG;
+  int res[HMRT_MAX_LEVELS];
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, nullptr, nullptr);
+  if (rc) return rc;
+  hmrt::Grid& g = ctx->grid;
+  g.pyramid = d_pyramid;
+  g.color_map = reinterpret_cast<const uint8_t*>(d_color_map);
+  g.coarse_res = coarse_res;
+  g.coarse_sq = (uint32_t)coarse_res * (uint32_t)coarse_res;
+  g.levels = levels;
+  g.res0 = res[0];
+  /* point_buffer_resolution->x * pow(2.f, LOD_levels - 1) (CudaKernel.cu:134): exact, < 2^24 */
+  g.extent = (float)coarse_res * (float)(1 << (levels - 1));
+  ctx->init_max_height = max_height;
+  ctx->have_grid = true;
+  return 0;
+}
+
+int hmrt_clear_heightmap(hmrt_ctx* ctx) {
+  if (!ctx) return HMRT_E_ARG;
+  ctx->have_grid = false;
+  memset(&ctx->grid, 0, sizeof(ctx->grid));
+  return 0;
+}
+
+void hmrt_trace_opts_default(hmrt_trace_opts* o, float max_height) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_height = max_height;
+  o->light_dir[0] = 0.0f;
+  o->light_dir[1] = 1.0f;
+  o->light_dir[2] = 0.0f;
+  o->shadow_bias = 0.0625f;
+  o->tile_first = 0;
+  o->tile_stride = 1;
+}
+
+int hmrt_rows_local(int H, int tile_first, int tile_stride) {
+  if (H < 1 || tile_first < 0) return HMRT_E_ARG;
+  return hmrt::rows_local(H, tile_first, tile_stride);
+}
+
+int64_t hmrt_launch_count(const hmrt_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+/* Internal declarations shared by the translation units of libhmrt.so (not installed). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ray_core.cuh"
+
+#define HMRT_CUDA(call)                          \
+  do {                                           \
+    cudaError_t e_ = (call);                     \
+    if (e_ != cudaSuccess) return (int)e_;       \
+  } while (0)
+
+/* kernel launches are checked with cudaGetLastError (cudaPeekAtLastError keeps sticky errors) */
+#define HMRT_LAUNCHED(ctx)                       \
+  do {                                           \
+    cudaError_t e_ = cudaGetLastError();         \
+    if (e_ != cudaSuccess) return (int)e_;       \
+    (ctx)->launches++;                           \
+  } while (0)
+
+struct hmrt_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  int64_t launches;
+  /* borrowed heightmap (hmrt_set_heightmap) */
+  bool have_grid;
+  hmrt::Grid grid;
+  float init_max_height;
+  /* per-frame constants for multi-frame launches */
+  hmrt::FrameConsts* d_frames;
+  int frames_cap;
+  /* context-owned framebuffer for hmrt_trace_host */
+  uint8_t* d_fb;
+  size_t fb_cap;
+};
+
+namespace hmrt {
+
+struct DeviceGuard {
+  int prev;
+  bool switched;
+  explicit DeviceGuard(int dev) : prev(-1), switched(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+int pyramid_layout(int coarse_res, int levels, int* res, int64_t* idx, int64_t* total);
+
+}  // namespace hmrt

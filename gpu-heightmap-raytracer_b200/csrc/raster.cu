@@ -1,0 +1,392 @@
+/*
+ * raster.cu -- point-cloud -> heightmap rasterisation and the max-mipmap build.
+ *
+ * CPU semantics being replaced: the inner loop of loadLASToSection
+ * (GPUHeightmapRaytracer/src/main.cpp:193-234).  Per point the reference computes the finest
+ * cell, skips out-of-section / class-7 points, writes the colour (last writer in file order
+ * wins, :223-224) and pushes max(z) up all pyramid levels with an early break (:227-233).
+ * Because parent >= child is an invariant of that loop and sections start at +0.0f (:259),
+ * its fixed point is
+ *     finest = max over points (floored at +0),   level i+1 = max of 2x2 children,
+ * independent of point order.  Hence two kernels:
+ *   (a) scatter: one thread per point, RED.MAX on the int view of the finest level
+ *       (non-negative floats order like their bit patterns) -> bit-exact, order-independent;
+ *       colours go through a 64-bit (file index, rgb) key so "last writer wins" is deterministic;
+ *   (b) mip build: one 128x128 finest tile per CTA, all 7 coarser levels in one pass.
+ */
+#include <string.h>
+
+#include "hmrt_internal.cuh"
+
+namespace hmrt {
+
+constexpr int kScatterThreads = 256;
+
+struct ScatterParams {
+  double scale[3], offset[3], mn[3];
+  float cell[3];
+  float origin[2];
+  int res0;
+  int cls_off; /* byte offset of the classification byte, -1: none */
+  int rgb_off; /* byte offset of R (u16 x 3), -1: none */
+};
+
+/* CudaSpace::Color(unsigned short...) : floor(c / 65535.f * 255.f)  (CudaKernel.cuh:41-46) */
+__device__ __forceinline__ uint32_t color16(uint32_t c) {
+  return (uint32_t)__float2int_rz(floorf(__fmul_rn(__fdiv_rn((float)c, 65535.0f), 255.0f))) & 0xffu;
+}
+
+/* main.cpp:200-233 for one decoded point (gx, gy, gz = liblas Point::GetX/Y/Z in double) */
+__device__ __forceinline__ void bin_point(const ScatterParams& sp, double gx, double gy, double gz, int cls,
+                                          uint32_t rgb, int64_t file_index, int* __restrict__ finest,
+                                          unsigned long long* __restrict__ keys) {
+  const float fX = __fdiv_rn(__double2float_rn(__dsub_rn(gx, sp.mn[0])), sp.cell[0]); /* :200 */
+  const float fY = __fdiv_rn(__double2float_rn(__dsub_rn(gy, sp.mn[1])), sp.cell[1]); /* :201 */
+  const float fZ = __fdiv_rn(__double2float_rn(__dsub_rn(gz, sp.mn[2])), sp.cell[2]); /* :202 */
+  const float dx = floorf(__fsub_rn(fX, sp.origin[0]));                               /* :205 */
+  const float dy = floorf(__fsub_rn(fY, sp.origin[1]));                               /* :206 */
+  const float r0 = (float)sp.res0;
+  if (!(dx >= 0.0f && dx < r0 && dy >= 0.0f && dy < r0) || cls == 7) return;          /* :209 */
+  const size_t cell = (size_t)(int)dx + (size_t)(int)dy * (size_t)sp.res0;
+  if (keys) /* :223-224; +1 so that key 0 means "never written" */
+    atomicMax(keys + cell, ((unsigned long long)(file_index + 1) << 24) | rgb);
+  /* :227-233 at level 0.  Negative or NaN heights never replace the +0 floor in the
+   * reference (`buf <= fZ` is false), -0.0f maps to INT_MIN and is a no-op here. */
+  if (fZ >= 0.0f) atomicMax(finest + cell, __float_as_int(fZ));
+}
+
+__device__ __forceinline__ int32_t ld_i32_bytes(const uint8_t* p) {
+  return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+}
+
+/*
+ * LAS records: a CTA streams its 256 consecutive records (256 * record_len contiguous bytes)
+ * into shared memory with 16-byte loads, then each thread decodes its own record from there:
+ * the global reads are fully coalesced even for the odd 26/34-byte record sizes.
+ */
+__global__ void __launch_bounds__(kScatterThreads)
+scatter_las_kernel(const uint8_t* __restrict__ records, int64_t n, int record_len, const __grid_constant__ ScatterParams sp,
+                   int64_t first_index, int* __restrict__ finest, unsigned long long* __restrict__ keys, int staged) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int64_t first = (int64_t)blockIdx.x * kScatterThreads;
+  const int64_t i = first + threadIdx.x;
+  const uint8_t* rec;
+  if (staged) {
+    const int64_t remaining = n - first;
+    const int count = remaining < kScatterThreads ? (int)remaining : kScatterThreads;
+    const int bytes = count * record_len;
+    const uint8_t* src = records + first * record_len; /* 16-byte aligned: 256*record_len % 16 == 0 */
+    const int vec = bytes >> 4;
+    for (int v = threadIdx.x; v < vec; v += kScatterThreads)
+      reinterpret_cast<uint4*>(smem)[v] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    for (int b = (vec << 4) + threadIdx.x; b < bytes; b += kScatterThreads) smem[b] = __ldg(src + b);
+    __syncthreads();
+    rec = smem + threadIdx.x * record_len;
+  } else {
+    rec = records + i * record_len;
+  }
+  if (i >= n) return;
+  /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
+  const double gx = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec), sp.scale[0]), sp.offset[0]);
+  const double gy = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 4), sp.scale[1]), sp.offset[1]);
+  const double gz = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 8), sp.scale[2]), sp.offset[2]);
+  const int cls = sp.cls_off >= 0 ? (rec[sp.cls_off] & 0x1f) : 0; /* Classification::GetClass() */
+  uint32_t rgb = 0;
+  if (keys && sp.rgb_off >= 0) {
+    const uint8_t* c = rec + sp.rgb_off;
+    const uint32_t r = c[0] | (c[1] << 8), g = c[2] | (c[3] << 8), b = c[4] | (c[5] << 8);
+    rgb = (color16(r) << 16) | (color16(g) << 8) | color16(b);
+  }
+  bin_point(sp, gx, gy, gz, cls, rgb, first_index + i, finest, keys);
+}
+
+/* PointdataGenerator output: float32 x y z triples; 3 coalesced loads per thread */
+__global__ void __launch_bounds__(kScatterThreads)
+scatter_xyz_kernel(const float* __restrict__ xyz, int64_t n, const __grid_constant__ ScatterParams sp,
+                   int* __restrict__ finest) {
+  __shared__ float s[kScatterThreads * 3];
+  const int64_t first = (int64_t)blockIdx.x * kScatterThreads;
+  const int64_t remaining = n - first;
+  const int count = remaining < kScatterThreads ? (int)remaining : kScatterThreads;
+  for (int k = threadIdx.x; k < count * 3; k += kScatterThreads) s[k] = __ldg(xyz + first * 3 + k);
+  __syncthreads();
+  if (threadIdx.x >= count) return;
+  const float x = s[threadIdx.x * 3], y = s[threadIdx.x * 3 + 1], z = s[threadIdx.x * 3 + 2];
+  bin_point(sp, (double)x, (double)y, (double)z, 0, 0, 0, finest, nullptr);
+}
+
+__global__ void resolve_colors_kernel(const unsigned long long* __restrict__ keys, uint8_t* __restrict__ cmap,
+                                      int64_t n_cells) {
+  /* each thread packs 4 cells = 12 bytes = 3 words, so the stores are 4-byte and coalesced */
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c0 = q * 4;
+  if (c0 >= n_cells) return;
+  if (c0 + 4 <= n_cells) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (uint32_t)(__ldg(keys + c0 + k) & 0xffffffull);
+    /* byte order r,g,b per cell; v = r<<16 | g<<8 | b */
+    uint8_t bytes[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bytes[3 * k] = (v[k] >> 16) & 0xff;
+      bytes[3 * k + 1] = (v[k] >> 8) & 0xff;
+      bytes[3 * k + 2] = v[k] & 0xff;
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(cmap + c0 * 3); /* c0*3 is a multiple of 12 */
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+      dst[w] = bytes[4 * w] | (bytes[4 * w + 1] << 8) | (bytes[4 * w + 2] << 16) | ((uint32_t)bytes[4 * w + 3] << 24);
+  } else {
+    for (int64_t c = c0; c < n_cells; ++c) {
+      const uint32_t v = (uint32_t)(__ldg(keys + c) & 0xffffffull);
+      cmap[c * 3] = (v >> 16) & 0xff;
+      cmap[c * 3 + 1] = (v >> 8) & 0xff;
+      cmap[c * 3 + 2] = v & 0xff;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Max-mipmap build.  Fused kernel: CTA = 512 threads = one 128 x 128 tile of the finest level.
+ * Warp w owns finest rows [8w, 8w+8), lane l owns columns [4l, 4l+4): eight 16-byte loads per
+ * thread (each warp-load is one fully coalesced 512-byte row segment), levels 1 and 2 come
+ * straight out of registers, level 3 needs one warp shuffle, levels 4..7 are reduced by the
+ * first warps through shared memory.  Every level is written once, nothing is re-read from HBM:
+ * traffic = 4*R0^2 read + 4*R0^2/3 written (the algorithmic minimum).
+ */
+struct MipParams {
+  float* pyramid;
+  int64_t idx[8]; /* float offsets of levels 0..7 (unused entries = 0) */
+  int res0;
+  int out_levels; /* how many coarser levels to write: min(levels - 1, 7) */
+};
+
+__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
+
+__global__ void __launch_bounds__(512) build_mips_fused_kernel(const __grid_constant__ MipParams mp) {
+  __shared__ float s3[16][17];
+  __shared__ float s4[8][9];
+  __shared__ float s5[4][5];
+  __shared__ float s6[2][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile_x = blockIdx.x, tile_z = blockIdx.y;
+  const int R0 = mp.res0;
+  const float* l0 = mp.pyramid + mp.idx[0];
+  const int z0 = tile_z * 128 + warp * 8, x0 = tile_x * 128 + lane * 4;
+
+  float4 a[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) a[r] = __ldg(reinterpret_cast<const float4*>(l0 + (size_t)(z0 + r) * R0 + x0));
+
+  float m2[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) { /* two groups of 4 rows */
+    float m1[2][2];
+#pragma unroll
+    for (int rp = 0; rp < 2; ++rp) {
+      const float4 u = a[h * 4 + rp * 2], v = a[h * 4 + rp * 2 + 1];
+      m1[rp][0] = max4(u.x, u.y, v.x, v.y);
+      m1[rp][1] = max4(u.z, u.w, v.z, v.w);
+      if (mp.out_levels >= 1) {
+        float* l1 = mp.pyramid + mp.idx[1];
+        const int z1 = tile_z * 64 + warp * 4 + h * 2 + rp, x1 = tile_x * 64 + lane * 2;
+        *reinterpret_cast<float2*>(l1 + (size_t)z1 * (R0 >> 1) + x1) = make_float2(m1[rp][0], m1[rp][1]);
+      }
+    }
+    m2[h] = max4(m1[0][0], m1[0][1], m1[1][0], m1[1][1]);
+    if (mp.out_levels >= 2) {
+      float* l2 = mp.pyramid + mp.idx[2];
+      const int z2 = tile_z * 32 + warp * 2 + h, x2 = tile_x * 32 + lane;
+      l2[(size_t)z2 * (R0 >> 2) + x2] = m2[h];
+    }
+  }
+  if (mp.out_levels < 3) return;
+  float m3 = fmaxf(m2[0], m2[1]);
+  m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, 1));
+  if ((lane & 1) == 0) {
+    float* l3 = mp.pyramid + mp.idx[3];
+    const int z3 = tile_z * 16 + warp, x3 = tile_x * 16 + (lane >> 1);
+    l3[(size_t)z3 * (R0 >> 3) + x3] = m3;
+    s3[warp][lane >> 1] = m3;
+  }
+  if (mp.out_levels < 4) return;
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < 64) {
+    const int z = t >> 3, x = t & 7;
+    const float m = max4(s3[2 * z][2 * x], s3[2 * z][2 * x + 1], s3[2 * z + 1][2 * x], s3[2 * z + 1][2 * x + 1]);
+    s4[z][x] = m;
+    (mp.pyramid + mp.idx[4])[(size_t)(tile_z * 8 + z) * (R0 >> 4) + tile_x * 8 + x] = m;
+  }
+  if (mp.out_levels < 5) return;
+  __syncthreads();
+  if (t < 16) {
+    const int z = t >> 2, x = t & 3;
+    const float m = max4(s4[2 * z][2 * x], s4[2 * z][2 * x + 1], s4[2 * z + 1][2 * x], s4[2 * z + 1][2 * x + 1]);
+    s5[z][x] = m;
+    (mp.pyramid + mp.idx[5])[(size_t)(tile_z * 4 + z) * (R0 >> 5) + tile_x * 4 + x] = m;
+  }
+  if (mp.out_levels < 6) return;
+  __syncthreads();
+  if (t < 4) {
+    const int z = t >> 1, x = t & 1;
+    const float m = max4(s5[2 * z][2 * x], s5[2 * z][2 * x + 1], s5[2 * z + 1][2 * x], s5[2 * z + 1][2 * x + 1]);
+    s6[z][x] = m;
+    (mp.pyramid + mp.idx[6])[(size_t)(tile_z * 2 + z) * (R0 >> 6) + tile_x * 2 + x] = m;
+  }
+  if (mp.out_levels < 7) return;
+  __syncthreads();
+  if (t == 0)
+    (mp.pyramid + mp.idx[7])[(size_t)tile_z * (R0 >> 7) + tile_x] = max4(s6[0][0], s6[0][1], s6[1][0], s6[1][1]);
+}
+
+/* generic one-level step (grids that do not tile by 128, and levels beyond the 8th) */
+__global__ void build_mip_level_kernel(const float* __restrict__ fine, float* __restrict__ coarse, int rc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= rc || z >= rc) return;
+  const size_t rf = (size_t)rc * 2;
+  const float2 u = __ldg(reinterpret_cast<const float2*>(fine + (size_t)(2 * z) * rf + 2 * x));
+  const float2 v = __ldg(reinterpret_cast<const float2*>(fine + (size_t)(2 * z + 1) * rf + 2 * x));
+  coarse[(size_t)z * rc + x] = max4(u.x, u.y, v.x, v.y);
+}
+
+static int fill_scatter_params(const hmrt_las_transform* xf, int res0, ScatterParams& sp) {
+  for (int i = 0; i < 3; ++i) {
+    sp.scale[i] = xf->scale[i];
+    sp.offset[i] = xf->offset[i];
+    sp.mn[i] = xf->min[i];
+    sp.cell[i] = xf->cell_size[i];
+    if (!(xf->cell_size[i] > 0.0f)) return HMRT_E_ARG;
+  }
+  sp.origin[0] = xf->origin[0];
+  sp.origin[1] = xf->origin[1];
+  sp.res0 = res0;
+  sp.cls_off = -1;
+  sp.rgb_off = -1;
+  return 0;
+}
+
+}  // namespace hmrt
+
+extern "C" {
+
+int hmrt_clear_section(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int levels, uint64_t* d_color_keys,
+                       hmrt_color* d_color_map) {
+  if (!ctx || !d_pyramid) return HMRT_E_ARG;
+  int res[HMRT_MAX_LEVELS];
+  int64_t total = 0;
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, nullptr, &total);
+  if (rc) return rc;
+  hmrt::DeviceGuard guard(ctx->device);
+  const size_t cells = (size_t)res[0] * res[0];
+  HMRT_CUDA(cudaMemsetAsync(d_pyramid, 0, sizeof(float) * (size_t)total, ctx->stream)); /* main.cpp:259 */
+  if (d_color_keys) HMRT_CUDA(cudaMemsetAsync(d_color_keys, 0, sizeof(uint64_t) * cells, ctx->stream));
+  if (d_color_map) HMRT_CUDA(cudaMemsetAsync(d_color_map, 0, 3 * cells, ctx->stream)); /* main.cpp:260 */
+  return 0;
+}
+
+int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, int point_format,
+                     const hmrt_las_transform* xf, int64_t first_index, float* d_pyramid, int coarse_res, int levels,
+                     uint64_t* d_color_keys) {
+  static const int min_len[4] = {20, 28, 26, 34};
+  static const int rgb_off[4] = {-1, -1, 20, 28};
+  if (!ctx || !xf || !d_pyramid || n < 0 || first_index < 0) return HMRT_E_ARG;
+  if (point_format < 0 || point_format > 3 || record_len < min_len[point_format] || record_len > 65535)
+    return HMRT_E_ARG;
+  if (n > 0 && !d_records) return HMRT_E_ARG;
+  if (first_index + n >= ((int64_t)1 << 40)) return HMRT_E_ARG; /* key = index << 24 | rgb */
+  int res[HMRT_MAX_LEVELS];
+  int64_t idx[HMRT_MAX_LEVELS];
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, idx, nullptr);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  hmrt::ScatterParams sp;
+  rc = hmrt::fill_scatter_params(xf, res[0], sp);
+  if (rc) return rc;
+  sp.cls_off = 15;
+  sp.rgb_off = rgb_off[point_format];
+  hmrt::DeviceGuard guard(ctx->device);
+  const int64_t blocks = (n + hmrt::kScatterThreads - 1) / hmrt::kScatterThreads;
+  if (blocks > 0x7fffffffLL) return HMRT_E_SHAPE;
+  const size_t smem = (size_t)hmrt::kScatterThreads * record_len;
+  const int staged = (smem <= 48 * 1024) && ((reinterpret_cast<uintptr_t>(d_records) & 15) == 0);
+  hmrt::scatter_las_kernel<<<(unsigned)blocks, hmrt::kScatterThreads, staged ? smem : 0, ctx->stream>>>(
+      d_records, n, record_len, sp, first_index, reinterpret_cast<int*>(d_pyramid + idx[0]),
+      reinterpret_cast<unsigned long long*>(d_color_keys), staged);
+  HMRT_LAUNCHED(ctx);
+  return 0;
+}
+
+int hmrt_scatter_xyz(hmrt_ctx* ctx, const float* d_xyz, int64_t n, const hmrt_las_transform* xf, float* d_pyramid,
+                     int coarse_res, int levels) {
+  if (!ctx || !xf || !d_pyramid || n < 0) return HMRT_E_ARG;
+  if (n > 0 && !d_xyz) return HMRT_E_ARG;
+  int res[HMRT_MAX_LEVELS];
+  int64_t idx[HMRT_MAX_LEVELS];
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, idx, nullptr);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  hmrt::ScatterParams sp;
+  rc = hmrt::fill_scatter_params(xf, res[0], sp);
+  if (rc) return rc;
+  hmrt::DeviceGuard guard(ctx->device);
+  const int64_t blocks = (n + hmrt::kScatterThreads - 1) / hmrt::kScatterThreads;
+  if (blocks > 0x7fffffffLL) return HMRT_E_SHAPE;
+  hmrt::scatter_xyz_kernel<<<(unsigned)blocks, hmrt::kScatterThreads, 0, ctx->stream>>>(
+      d_xyz, n, sp, reinterpret_cast<int*>(d_pyramid + idx[0]));
+  HMRT_LAUNCHED(ctx);
+  return 0;
+}
+
+int hmrt_build_mips(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int levels) {
+  if (!ctx || !d_pyramid) return HMRT_E_ARG;
+  int res[HMRT_MAX_LEVELS];
+  int64_t idx[HMRT_MAX_LEVELS];
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, idx, nullptr);
+  if (rc) return rc;
+  if (levels == 1) return 0;
+  hmrt::DeviceGuard guard(ctx->device);
+  int done = 0; /* coarser levels already built */
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_pyramid + idx[0]) & 15) == 0;
+  if (res[0] % 128 == 0 && aligned) {
+    hmrt::MipParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.pyramid = d_pyramid;
+    mp.res0 = res[0];
+    mp.out_levels = levels - 1 < 7 ? levels - 1 : 7;
+    for (int i = 0; i <= mp.out_levels; ++i) mp.idx[i] = idx[i];
+    /* float2 stores into level 1 need 8-byte alignment of its base: idx[1] is a sum of even squares
+     * for every level below the top, but the top level's own square may be odd */
+    const bool l1_aligned = (reinterpret_cast<uintptr_t>(d_pyramid + idx[1]) & 7) == 0;
+    if (l1_aligned) {
+      const dim3 grid(res[0] / 128, res[0] / 128);
+      hmrt::build_mips_fused_kernel<<<grid, 512, 0, ctx->stream>>>(mp);
+      HMRT_LAUNCHED(ctx);
+      done = mp.out_levels;
+    }
+  }
+  for (int l = done + 1; l < levels; ++l) {
+    const dim3 block(32, 8);
+    const dim3 grid((res[l] + 31) / 32, (res[l] + 7) / 8);
+    hmrt::build_mip_level_kernel<<<grid, block, 0, ctx->stream>>>(d_pyramid + idx[l - 1], d_pyramid + idx[l], res[l]);
+    HMRT_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+int hmrt_resolve_colors(hmrt_ctx* ctx, const uint64_t* d_color_keys, hmrt_color* d_color_map, int64_t n_cells) {
+  if (!ctx || !d_color_keys || !d_color_map || n_cells < 0) return HMRT_E_ARG;
+  if (n_cells == 0) return 0;
+  if (reinterpret_cast<uintptr_t>(d_color_map) & 3) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  const int64_t quads = (n_cells + 3) / 4;
+  const int64_t blocks = (quads + 255) / 256;
+  if (blocks > 0x7fffffffLL) return HMRT_E_SHAPE;
+  hmrt::resolve_colors_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+      reinterpret_cast<const unsigned long long*>(d_color_keys), reinterpret_cast<uint8_t*>(d_color_map), n_cells);
+  HMRT_LAUNCHED(ctx);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Context: one device, one stream -- the Python face of hmrt_ctx (include/hmrt.h).
+
+Method names follow the C ABI, which in turn mirrors the reference's host interface
+(CudaSpace::initializeDeviceVariables / rayTrace / freeDeviceVariables, CudaKernel.cuh:49-51,
+and the loadLASToSection loop, main.cpp:174-244).  Tensors are torch CUDA tensors used purely as
+device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import Camera, LasTransform, TraceOpts, check
+
+
+def pyramid_layout(coarse_res: int, levels: int):
+    """(res[levels], idx[levels], total floats) -- main.cpp:995-1003 via hmrt_pyramid_layout."""
+    lib = _abi.load()
+    res = (C.c_int * levels)()
+    idx = (C.c_int64 * levels)()
+    total = C.c_int64()
+    check(lib.hmrt_pyramid_layout(coarse_res, levels, res, idx, C.byref(total)), "hmrt_pyramid_layout")
+    return list(res), list(idx), total.value
+
+
+def rows_local(H: int, tile_first: int = 0, tile_stride: int = 1) -> int:
+    r = _abi.load().hmrt_rows_local(H, tile_first, tile_stride)
+    if r < 0:
+        raise _abi.HmrtError(r, "hmrt_rows_local")
+    return r
+
+
+def camera(position, forward, frame_dim=(32.0, 18.0, 20.0), normalize=True) -> Camera:
+    """Camera as the reference holds it: frame_dimension (main.cpp:57), unit camera_forward
+    (main.cpp:56), grid_camera_position in finest-cell units."""
+    f = np.asarray(forward, dtype=np.float64)
+    if normalize:
+        f = f / np.linalg.norm(f)
+    f = f.astype(np.float32)
+    cam = Camera()
+    cam.frame_dim[:] = [float(np.float32(v)) for v in frame_dim]
+    cam.forward[:] = [float(v) for v in f]
+    cam.position[:] = [float(np.float32(v)) for v in position]
+    return cam
+
+
+def trace_opts(max_height: float, use_color_map: bool = False, shadows: bool = False,
+               light_dir=(0.3, 0.8, 0.52), shadow_bias: float = 0.0, tile_first: int = 0,
+               tile_stride: int = 1) -> TraceOpts:
+    o = TraceOpts()
+    _abi.load().hmrt_trace_opts_default(C.byref(o), float(np.float32(max_height)))
+    o.use_color_map = int(bool(use_color_map))
+    o.shadows = int(bool(shadows))
+    l = np.asarray(light_dir, dtype=np.float64)
+    l = (l / np.linalg.norm(l)).astype(np.float32)
+    o.light_dir[:] = [float(v) for v in l]
+    o.shadow_bias = float(shadow_bias)
+    o.tile_first = int(tile_first)
+    o.tile_stride = int(tile_stride)
+    return o
+
+
+def _cam_array(cameras) -> "C.Array[Camera]":
+    if isinstance(cameras, Camera):
+        cameras = [cameras]
+    if isinstance(cameras, C.Array):
+        return cameras
+    cams = list(cameras)
+    arr = (Camera * len(cams))()
+    for i, c in enumerate(cams):
+        C.memmove(C.byref(arr, i * C.sizeof(Camera)), C.byref(c), C.sizeof(Camera))
+    return arr
+
+
+class Context:
+    def __init__(self, device: int | None = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("hmrt.Context needs a CUDA device: this path has no CPU fallback")
+        self._torch = torch
+        self.lib = _abi.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        check(self.lib.hmrt_create(self.device, C.byref(h)), "hmrt_create")
+        self._h = h
+        self._keep = None  # tensors borrowed by set_heightmap
+        self.grid = None   # (coarse_res, levels)
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _bind_stream(self):
+        s = self._torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.hmrt_set_stream(self._h, C.c_void_p(s)), "hmrt_set_stream")
+
+    def _dev(self, t, dtype, what):
+        torch = self._torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device.index == self.device):
+            raise TypeError(f"{what}: expected a CUDA tensor on device {self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise TypeError(f"{what}: expected a contiguous {dtype} tensor, got {t.dtype}")
+        return C.c_void_p(t.data_ptr())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hmrt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self.lib.hmrt_synchronize(self._h), "hmrt_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hmrt_launch_count(self._h))
+
+    # -- ray traversal ---------------------------------------------------------------------
+    def set_heightmap(self, pyramid, color_map, coarse_res: int, levels: int, max_height: float):
+        """== CudaSpace::initializeDeviceVariables (CudaKernel.cuh:50)."""
+        torch = self._torch
+        _, _, total = pyramid_layout(coarse_res, levels)
+        p = self._dev(pyramid, torch.float32, "pyramid")
+        if pyramid.numel() < total:
+            raise ValueError(f"pyramid has {pyramid.numel()} floats, layout needs {total}")
+        cm = None
+        if color_map is not None:
+            cm = self._dev(color_map, torch.uint8, "color_map")
+            r0 = coarse_res << (levels - 1)
+            if color_map.numel() < r0 * r0 * 3:
+                raise ValueError("color_map too small")
+        check(self.lib.hmrt_set_heightmap(self._h, p, cm, coarse_res, levels, float(max_height)), "hmrt_set_heightmap")
+        self._keep = (pyramid, color_map)
+        self.grid = (coarse_res, levels)
+
+    def clear_heightmap(self):
+        """== CudaSpace::freeDeviceVariables (CudaKernel.cuh:51)."""
+        check(self.lib.hmrt_clear_heightmap(self._h), "hmrt_clear_heightmap")
+        self._keep = None
+        self.grid = None
+
+    def trace(self, W: int, H: int, cameras, opts: TraceOpts, out=None, hits=False):
+        """== CudaSpace::rayTrace (CudaKernel.cuh:49) for one or many cameras in one launch.
+        Returns (rgb uint8 [frames, rows_local, W, 3], hits int32 [frames, rows_local, W, 4] | None);
+        asynchronous on torch's current stream."""
+        torch = self._torch
+        cams = _cam_array(cameras)
+        n = len(cams)
+        rows = rows_local(H, opts.tile_first, opts.tile_stride)
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = torch.empty((n, rows, W, 3), dtype=torch.uint8, device=dev)
+        elif out.numel() < n * rows * W * 3:
+            raise ValueError("out too small")
+        hit_t = None
+        if hits is True:
+            hit_t = torch.zeros((n, rows, W, 4), dtype=torch.int32, device=dev)
+        elif hits not in (False, None):
+            hit_t = hits
+        self._bind_stream()
+        check(self.lib.hmrt_trace(self._h, W, H, cams, n, C.byref(opts), self._dev(out, torch.uint8, "out"),
+                                  self._dev(hit_t, torch.int32, "hits") if hit_t is not None else None), "hmrt_trace")
+        return out, hit_t
+
+    def trace_host(self, W: int, H: int, cameras, opts: TraceOpts, out_host):
+        """Host-buffer variant (hmrt_trace_host): out_host is a (pinned) CPU uint8 tensor/array."""
+        cams = _cam_array(cameras)
+        n = len(cams)
+        rows = rows_local(H, opts.tile_first, opts.tile_stride)
+        need = n * rows * W * 3
+        if hasattr(out_host, "data_ptr"):
+            if out_host.is_cuda or out_host.numel() < need or not out_host.is_contiguous():
+                raise ValueError("out_host must be a contiguous CPU uint8 tensor of sufficient size")
+            ptr = out_host.data_ptr()
+        else:
+            if out_host.nbytes < need:
+                raise ValueError("out_host too small")
+            ptr = out_host.ctypes.data
+        self._bind_stream()
+        check(self.lib.hmrt_trace_host(self._h, W, H, cams, n, C.byref(opts), C.c_void_p(ptr)), "hmrt_trace_host")
+        return out_host
+
+    # -- rasterisation ---------------------------------------------------------------------
+    def clear_section(self, pyramid, coarse_res: int, levels: int, color_keys=None, color_map=None):
+        torch = self._torch
+        self._bind_stream()
+        check(self.lib.hmrt_clear_section(
+            self._h, self._dev(pyramid, torch.float32, "pyramid"), coarse_res, levels,
+            self._dev(color_keys, torch.int64, "color_keys") if color_keys is not None else None,
+            self._dev(color_map, torch.uint8, "color_map") if color_map is not None else None), "hmrt_clear_section")
+
+    def scatter_las(self, records, n: int, record_len: int, point_format: int, xf: LasTransform, pyramid,
+                    coarse_res: int, levels: int, first_index: int = 0, color_keys=None):
+        torch = self._torch
+        self._bind_stream()
+        if n > 0 and records.numel() < n * record_len:
+            raise ValueError("records tensor too small")
+        check(self.lib.hmrt_scatter_las(
+            self._h, self._dev(records, torch.uint8, "records") if n > 0 else None, n, record_len, point_format,
+            C.byref(xf), first_index, self._dev(pyramid, torch.float32, "pyramid"), coarse_res, levels,
+            self._dev(color_keys, torch.int64, "color_keys") if color_keys is not None else None), "hmrt_scatter_las")
+
+    def scatter_xyz(self, xyz, n: int, xf: LasTransform, pyramid, coarse_res: int, levels: int):
+        torch = self._torch
+        self._bind_stream()
+        if n > 0 and xyz.numel() < 3 * n:
+            raise ValueError("xyz tensor too small")
+        check(self.lib.hmrt_scatter_xyz(self._h, self._dev(xyz, torch.float32, "xyz") if n > 0 else None, n, C.byref(xf),
+                                        self._dev(pyramid, torch.float32, "pyramid"), coarse_res, levels), "hmrt_scatter_xyz")
+
+    def build_mips(self, pyramid, coarse_res: int, levels: int):
+        self._bind_stream()
+        check(self.lib.hmrt_build_mips(self._h, self._dev(pyramid, self._torch.float32, "pyramid"), coarse_res, levels),
+              "hmrt_build_mips")
+
+    def resolve_colors(self, color_keys, color_map, n_cells: int):
+        torch = self._torch
+        self._bind_stream()
+        check(self.lib.hmrt_resolve_colors(self._h, self._dev(color_keys, torch.int64, "color_keys"),
+                                           self._dev(color_map, torch.uint8, "color_map"), n_cells), "hmrt_resolve_colors")

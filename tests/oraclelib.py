@@ -179,3 +179,101 @@ def hit_cells(hits: np.ndarray, r0: int):
 
 def steps_of(hits: np.ndarray) -> np.ndarray:
     return hits["flags"] >> 8
+
+
+# ---------------------------------------------------------------------------------------------
+# hostsim: the product's ray_core.cuh compiled for the host (tests/hostsim/hostsim.cpp)
+
+HOSTSIM_SO = REPO / "tests" / "_build" / "libhmrt_hostsim.so"
+
+
+def hostsim() -> C.CDLL:
+    if "hostsim" not in _cache:
+        src = REPO / "tests" / "hostsim" / "hostsim.cpp"
+        core = REPO / "gpu-heightmap-raytracer_b200" / "csrc" / "ray_core.cuh"
+        if not HOSTSIM_SO.exists() or HOSTSIM_SO.stat().st_mtime < max(src.stat().st_mtime, core.stat().st_mtime):
+            HOSTSIM_SO.parent.mkdir(parents=True, exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-o", str(HOSTSIM_SO),
+                            str(src), "-lpthread"], check=True)
+        lib = C.CDLL(str(HOSTSIM_SO))
+        lib.hostsim_trace.restype = C.c_int
+        lib.hostsim_trace.argtypes = _TRACE_ARGS
+        _cache["hostsim"] = lib
+    return _cache["hostsim"]
+
+
+def assert_same_trace(a, b, what=""):
+    """Bit-exact comparison of two (rgb, hits) results; steps compared only if both sides count them."""
+    rgb_a, hit_a = a
+    rgb_b, hit_b = b
+    bad = int((rgb_a != rgb_b).any(axis=-1).sum())
+    assert bad == 0, f"{what}: {bad} pixels differ in colour"
+    if hit_a is not None and hit_b is not None:
+        for f in "xyz":
+            # compare bit patterns so that NaN == NaN
+            assert (hit_a[f].view(np.uint32) == hit_b[f].view(np.uint32)).all(), f"{what}: hit.{f} differs"
+        fa, fb = hit_a["flags"], hit_b["flags"]
+        assert ((fa & 0xFF) == (fb & 0xFF)).all(), f"{what}: hit flags differ"
+        if (fa >> 8).any() and (fb >> 8).any():
+            assert ((fa >> 8) == (fb >> 8)).all(), f"{what}: step counts differ"
+
+
+SCENES = {
+    # name: (R0, levels)
+    "r1024_l8": (1024, 8),
+    "r512_l4": (512, 4),
+    "r256_l1": (256, 1),
+    "r768_l7": (768, 7),   # coarse_res 12: not a power of two
+}
+
+
+def scene(name: str, seed: int = 0):
+    r0, levels = SCENES[name]
+    fin = sines_terrain(r0, seed)
+    pyr = pyramid_from_finest(fin, levels)
+    rng = np.random.default_rng(seed + 1)
+    cmap = rng.integers(0, 256, (r0, r0, 3), dtype=np.uint8)
+    return dict(r0=r0, levels=levels, coarse=r0 >> (levels - 1), finest=fin, pyramid=pyr, color_map=cmap,
+                max_height=float(fin.max()))
+
+
+def cameras_for(sc, n=4):
+    """Deterministic camera set: down-looking, oblique, grazing and upward, four headings."""
+    r0, mh = sc["r0"], sc["max_height"]
+    poses = [(-0.9, 1.5, (0.0, 1.0)), (-0.3, 1.5, (1.0, 0.3)), (-0.1, 1.2, (-0.7, -0.5)), (0.2, 0.5, (0.4, -1.0)),
+             (-0.5, 2.5, (-1.0, 0.05)), (-0.05, 1.05, (0.6, 0.8))]
+    return [make_camera((r0 / 2 + 0.37, k * mh, r0 / 2 - 3.21), (hx, pitch, hz)) for pitch, k, (hx, hz) in poses[:n]]
+
+
+def load_golden():
+    """tests/golden/ray_golden.npz -> dict with the pyramid rebuilt from the stored finest level."""
+    g = dict(np.load(REPO / "tests" / "golden" / "ray_golden.npz"))
+    levels = int(g["levels"])
+    g["pyramid"] = pyramid_from_finest(g["finest"], levels)
+    g["r0"] = g["finest"].shape[0]
+    g["coarse"] = g["r0"] >> (levels - 1)
+    cams = []
+    for row in g["cameras"]:
+        c = Camera()
+        c.frame_dim[:] = [float(v) for v in row[0:3]]
+        c.forward[:] = [float(v) for v in row[3:6]]
+        c.position[:] = [float(v) for v in row[6:9]]
+        cams.append(c)
+    g["cams"] = cams
+    return g
+
+
+GOLDEN_MODES = {"ramp": (False, False), "shadow": (False, True), "cmap": (True, False)}
+
+
+def golden_opts(g, mode):
+    uc, sh = GOLDEN_MODES[mode]
+    o = make_opts(float(g["max_height"]), use_color_map=uc, shadows=sh)
+    o.light_dir[:] = [float(v) for v in g["light_dir"]]
+    return o
+
+
+def golden_expected(g, mode, i):
+    hmode = "ramp" if mode == "cmap" else mode  # the walk does not depend on the colouring mode
+    hits = np.ascontiguousarray(g[f"hits_{hmode}_{i}"]).view(hit_dtype).reshape(int(g["H"]), int(g["W"]))
+    return g[f"rgb_{mode}_{i}"], hits
