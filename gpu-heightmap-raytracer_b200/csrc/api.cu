@@ -146,6 +146,12 @@ int hmrt_rows_local(int H, int tile_first, int tile_stride) {
   return hmrt::rows_local(H, tile_first, tile_stride);
 }
 
+int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;
+  ctx->trace_variant = variant;
+  return 0;
+}
+
 int64_t hmrt_launch_count(const hmrt_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 }  // extern "C"

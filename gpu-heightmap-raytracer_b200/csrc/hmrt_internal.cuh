@@ -24,6 +24,7 @@ struct hmrt_ctx {
   int sm_count;
   cudaStream_t stream;
   int64_t launches;
+  int trace_variant; /* 0 = production walk, 1 = operation-by-operation walk (diagnostic) */
   /* borrowed heightmap (hmrt_set_heightmap) */
   bool have_grid;
   hmrt::Grid grid;

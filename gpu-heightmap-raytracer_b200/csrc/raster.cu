@@ -246,9 +246,10 @@ __global__ void build_mip_level_kernel(const float* __restrict__ fine, float* __
   const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= rc || z >= rc) return;
   const size_t rf = (size_t)rc * 2;
-  const float2 u = __ldg(reinterpret_cast<const float2*>(fine + (size_t)(2 * z) * rf + 2 * x));
-  const float2 v = __ldg(reinterpret_cast<const float2*>(fine + (size_t)(2 * z + 1) * rf + 2 * x));
-  coarse[(size_t)z * rc + x] = max4(u.x, u.y, v.x, v.y);
+  /* scalar loads: a level base is only guaranteed 4-byte alignment (odd coarse_res) */
+  const float* r0 = fine + (size_t)(2 * z) * rf + 2 * x;
+  const float* r1 = r0 + rf;
+  coarse[(size_t)z * rc + x] = max4(__ldg(r0), __ldg(r0 + 1), __ldg(r1), __ldg(r1 + 1));
 }
 
 static int fill_scatter_params(const hmrt_las_transform* xf, int res0, ScatterParams& sp) {

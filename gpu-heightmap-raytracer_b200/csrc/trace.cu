@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "hmrt_internal.cuh"
+#include "ray_fast.cuh"
 
 namespace hmrt {
 
@@ -37,7 +38,9 @@ struct TraceParams {
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
 };
 
-template <bool HITS>
+/* FAST = production walk (ray_fast.cuh); !FAST = operation-by-operation walk (ray_core.cuh), kept as
+ * the in-library parity reference (hmrt_set_trace_variant). */
+template <bool HITS, bool FAST>
 __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kTileH][kTileW * 3];
 
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_cons
     } else {
       f = p.frame0;
     }
-    const RayResult r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
+    const RayResult r = FAST ? trace_pixel_fast(p.grid, p.shading, f, p.W, p.H, px, py)
+                             : trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
     stage[ty][tx * 3 + 0] = r.r;
     stage[ty][tx * 3 + 1] = r.g;
     stage[ty][tx * 3 + 2] = r.b;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_cons
 
 static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, int n_frames,
                         const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
-  if (!ctx || !cams || !opts || !d_rgb) return HMRT_E_ARG;
+  if (!ctx || !cams || !opts) return HMRT_E_ARG;
   if (!ctx->have_grid) return HMRT_E_STATE;
   if (W < 2 || H < 2 || n_frames < 1 || n_frames > 65535) return HMRT_E_ARG;
   if (opts->use_color_map && !ctx->grid.color_map) return HMRT_E_ARG;
@@ -111,6 +115,7 @@ static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, in
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + kTileH - 1) / kTileH;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
+  if (!d_rgb) return HMRT_E_ARG;
   const int local_tiles = (n_tiles - opts->tile_first + stride - 1) / stride;
   if (local_tiles > 65535) return HMRT_E_SHAPE;
 
@@ -155,10 +160,17 @@ static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, in
   }
 
   const dim3 grid((W + kTileW - 1) / kTileW, local_tiles, n_frames);
-  if (d_hits)
-    trace_tiles_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
-  else
-    trace_tiles_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(p);
+  if (ctx->trace_variant == 0) {
+    if (d_hits)
+      trace_tiles_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(p);
+    else
+      trace_tiles_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(p);
+  } else {
+    if (d_hits)
+      trace_tiles_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(p);
+    else
+      trace_tiles_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(p);
+  }
   HMRT_LAUNCHED(ctx);
   return 0;
 }

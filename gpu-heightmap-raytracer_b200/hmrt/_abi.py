@@ -80,6 +80,7 @@ PROTOTYPES = {
     "hmrt_scatter_xyz": (C.c_int, [_P, _P, C.c_int64, C.POINTER(LasTransform), _P, C.c_int, C.c_int]),
     "hmrt_build_mips": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "hmrt_resolve_colors": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "hmrt_set_trace_variant": (C.c_int, [_P, C.c_int]),
     "hmrt_launch_count": (C.c_int64, [_P]),
 }
 

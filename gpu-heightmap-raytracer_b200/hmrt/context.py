@@ -117,6 +117,10 @@ class Context:
     def synchronize(self):
         check(self.lib.hmrt_synchronize(self._h), "hmrt_synchronize")
 
+    def set_trace_variant(self, variant: int):
+        """0 = production kernel, 1 = operation-by-operation walk (diagnostic, must agree bit for bit)."""
+        check(self.lib.hmrt_set_trace_variant(self._h, int(variant)), "hmrt_set_trace_variant")
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.hmrt_launch_count(self._h))
@@ -161,7 +165,9 @@ class Context:
         hit_t = None
         if hits is True:
             hit_t = torch.zeros((n, rows, W, 4), dtype=torch.int32, device=dev)
-        elif hits not in (False, None):
+        elif isinstance(hits, torch.Tensor):
+            if hits.numel() < n * rows * W * 4:
+                raise ValueError("hits too small")
             hit_t = hits
         self._bind_stream()
         check(self.lib.hmrt_trace(self._h, W, H, cams, n, C.byref(opts), self._dev(out, torch.uint8, "out"),

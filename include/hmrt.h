@@ -187,6 +187,10 @@ int hmrt_resolve_colors(hmrt_ctx* ctx, const uint64_t* d_color_keys, hmrt_color*
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 
+/* Diagnostic: 0 (default) = production traversal kernel; 1 = the operation-by-operation walk that
+ * mirrors CudaKernel.cu:121-177 line by line (slower; the two must agree bit for bit). */
+int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant);
+
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t hmrt_launch_count(const hmrt_ctx* ctx);
 

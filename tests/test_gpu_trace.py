@@ -147,6 +147,32 @@ def test_error_codes(cuda_ctx):
     assert out.shape[1] == 0
 
 
+def test_production_kernel_equals_operation_by_operation_walk(cuda_ctx):
+    """hmrt_set_trace_variant(1) runs the walk that mirrors CudaKernel.cu:121-177 line by line (IEEE divides,
+    floorf, level tables); the production kernel (FADD.RM floor, 3-op division proven by tests/cuda/divcheck.cu,
+    carried level state) must agree with it bit for bit, including degenerate axis-aligned rays."""
+    import gpulib
+
+    sc = ol.scene("r1024_l8", seed=4)
+    keep = gpulib.upload_scene(cuda_ctx, sc)  # noqa: F841
+    W, H = 641, 360  # odd width: the centre column has dir.x == 0 for an axis-aligned camera
+    cams = ol.cameras_for(sc, 6) + [ol.make_camera((512.0, 1.4 * sc["max_height"], 512.0), (0.0, -0.4, 1.0)),
+                                    ol.make_camera((512.5, 1.4 * sc["max_height"], 300.0), (1.0, -0.3, 0.0)),
+                                    ol.make_camera((512.5, 3.0 * sc["max_height"], 512.5), (0.0, -1.0, 1e-6))]
+    opts = ol.make_opts(sc["max_height"], shadows=True, use_color_map=True)
+    try:
+        cuda_ctx.set_trace_variant(1)
+        slow = gpulib.gpu_trace(cuda_ctx, W, H, cams, opts)
+    finally:
+        cuda_ctx.set_trace_variant(0)
+    fast = gpulib.gpu_trace(cuda_ctx, W, H, cams, opts)
+    for i in range(len(cams)):
+        ol.assert_same_trace((fast[0][i], fast[1][i]), (slow[0][i], slow[1][i]), f"variant cam{i}")
+    # and both equal the oracle on the degenerate cameras
+    for i in (6, 7, 8):
+        ol.assert_same_trace((fast[0][i], fast[1][i]), _oracle(sc, W, H, cams[i], opts), f"degenerate cam{i}")
+
+
 def test_full_size_4k_over_16384(cuda_ctx):
     """BASELINE config 3 at full size: 3840x2160 over a 16384^2 map (1.43 GB pyramid, built on the GPU by
     the product's own mip kernel).  Size-independent properties + sampled rows against the oracle."""
