@@ -81,6 +81,7 @@ int hmrt_destroy(hmrt_ctx* ctx) {
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (ctx->d_frames) cudaFree(ctx->d_frames);
   if (ctx->d_fb) cudaFree(ctx->d_fb);
+  if (ctx->d_hmax) cudaFree(ctx->d_hmax);
   delete ctx;
   return (int)e;
 }

@@ -29,6 +29,7 @@ struct hmrt_ctx {
   bool have_grid;
   hmrt::Grid grid;
   float init_max_height;
+  uint32_t* d_hmax; /* max(top level) as an ordered key, refreshed before every trace launch */
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;
   int frames_cap;

@@ -36,13 +36,48 @@ struct TraceParams {
   int rows_local;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
+  const uint32_t* hmax_key; /* order-preserving key of max(top level), written by top_level_max_kernel */
 };
 
-/* FAST = production walk (ray_fast.cuh); !FAST = operation-by-operation walk (ray_core.cuh), kept as
- * the in-library parity reference (hmrt_set_trace_variant). */
-template <bool HITS, bool FAST>
+/* float <-> unsigned key with the same ordering (so an unsigned atomicMax is a float max) */
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+/*
+ * Maximum of the coarsest pyramid level, recomputed before every trace launch because the
+ * heightmap buffer is borrowed and may have been refilled by the caller (the reference re-uploads
+ * it every frame, main.cpp:623).  16 K floats for a 16384^2 map: a few microseconds.
+ * A NaN cell yields a NaN maximum, which simply disables the air phase.
+ */
+__global__ void __launch_bounds__(256) top_level_max_kernel(const float* __restrict__ top, uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t k = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) k = max(k, float_to_key(__ldg(top + i)));
+  k = __reduce_max_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0 && k) atomicMax(out, k);
+}
+
+/* WALK: kWalkFast* = production walk (ray_fast.cuh); kWalkReference = operation-by-operation walk
+ * (ray_core.cuh), kept as the in-library parity reference (hmrt_set_trace_variant). */
+enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2 };
+
+template <bool HITS, int WALK>
 __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kTileH][kTileW * 3];
+  __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
+  uint32_t tab = 0; /* shared-window address of the level table, pinned in a register */
+  float hmax = 0.0f;
+  if (WALK != kWalkReference) {
+    hmax = key_to_float(__ldg(p.hmax_key));
+    fill_level_table(level_tab, p.grid);
+    __syncthreads();
+    tab = (uint32_t)__cvta_generic_to_shared(level_tab);
+    asm volatile("" : "+r"(tab));
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   /* warp (wx, wy) in a 4 x 2 arrangement; lane (lx, ly) in an 8 x 4 arrangement */
@@ -66,8 +101,13 @@ __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_cons
     } else {
       f = p.frame0;
     }
-    const RayResult r = FAST ? trace_pixel_fast(p.grid, p.shading, f, p.W, p.H, px, py)
-                             : trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
+    RayResult r;
+    if (WALK == kWalkFastPow2)
+      r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+    else if (WALK == kWalkFast)
+      r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+    else
+      r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
     stage[ty][tx * 3 + 0] = r.r;
     stage[ty][tx * 3 + 1] = r.g;
     stage[ty][tx * 3 + 2] = r.b;
@@ -160,17 +200,28 @@ static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, in
   }
 
   const dim3 grid((W + kTileW - 1) / kTileW, local_tiles, n_frames);
-  if (ctx->trace_variant == 0) {
-    if (d_hits)
-      trace_tiles_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(p);
-    else
-      trace_tiles_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(p);
-  } else {
-    if (d_hits)
-      trace_tiles_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(p);
-    else
-      trace_tiles_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(p);
+  const bool pow2 = (ctx->grid.coarse_res & (ctx->grid.coarse_res - 1)) == 0;
+  const int walk = ctx->trace_variant != 0 ? kWalkReference : (pow2 ? kWalkFastPow2 : kWalkFast);
+  if (walk != kWalkReference) {
+    if (!ctx->d_hmax) HMRT_CUDA(cudaMalloc(&ctx->d_hmax, sizeof(uint32_t)));
+    HMRT_CUDA(cudaMemsetAsync(ctx->d_hmax, 0, sizeof(uint32_t), ctx->stream));
+    const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
+    const unsigned blocks = (unsigned)((n_top + 4095u) / 4096u);
+    top_level_max_kernel<<<blocks > 1184u ? 1184u : blocks, 256, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, ctx->d_hmax);
+    HMRT_LAUNCHED(ctx);
+    p.hmax_key = ctx->d_hmax;
   }
+#define HMRT_LAUNCH_TRACE(HITS_, WALK_) trace_tiles_kernel<HITS_, WALK_><<<grid, kThreads, 0, ctx->stream>>>(p)
+  if (d_hits) {
+    if (walk == kWalkFastPow2) HMRT_LAUNCH_TRACE(true, kWalkFastPow2);
+    else if (walk == kWalkFast) HMRT_LAUNCH_TRACE(true, kWalkFast);
+    else HMRT_LAUNCH_TRACE(true, kWalkReference);
+  } else {
+    if (walk == kWalkFastPow2) HMRT_LAUNCH_TRACE(false, kWalkFastPow2);
+    else if (walk == kWalkFast) HMRT_LAUNCH_TRACE(false, kWalkFast);
+    else HMRT_LAUNCH_TRACE(false, kWalkReference);
+  }
+#undef HMRT_LAUNCH_TRACE
   HMRT_LAUNCHED(ctx);
   return 0;
 }
