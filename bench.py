@@ -99,7 +99,7 @@ def terrain_cpu_rows(n_threads_hint=None):
 # ------------------------------------------------------------------------------------------------
 # clocks
 
-CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+CLOCK_QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
 
@@ -113,7 +113,10 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples whose timestamp falls inside [t_begin, t_end] (epoch seconds)."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -126,14 +129,18 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+                sm_v, mx_v = float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
+            sm.append(sm_v)
+            mx.append(mx_v)
+            for name, val in zip(names, f[6:10]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.path)
@@ -164,10 +171,14 @@ def cpu_sample_rate(pyramid_host: np.ndarray, max_height: float, step: int, budg
     opts = ol.make_opts(max_height)
     rgb = np.zeros((H, W, 3), np.uint8)
     rows_per_call = max(8, 2 * n_threads)
-    bands = [(b * (H // 8) + off) for off in range(0, H // 8, rows_per_call) for b in range(8)]
+    # bands interleaved over the frame height (sky and ground rows alike), cycling through the poses;
+    # several passes with shifted offsets so the budget, not the band list, ends the sample
+    bands = [(b * (H // 8) + off + shift) for shift in range(0, rows_per_call, 8) for off in range(0, H // 8, rows_per_call)
+             for b in range(8)]
+    bands = bands * len(cams)
     rays, t0 = 0, time.perf_counter()
     for j, r0 in enumerate(bands):
-        cam = cams[j % len(cams)]
+        cam = cams[(j // 8) % len(cams)]
         r1 = min(H, r0 + rows_per_call)
         rc = fn(pyramid_host.ctypes.data, None, COARSE, LEVELS, W, H, C.byref(cam), C.byref(opts), n_threads, r0, r1,
                 rgb.ctypes.data, None)
@@ -239,6 +250,7 @@ def run_gpu_arm(args):
     if world != args.gpus and rank == 0:
         print(f"bench.py: warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started early (nvidia-smi is slow to start); filtered to the timed window
     ctx = hmrt.Context(local)
     # heightmap: built on rank 0 with the product's kernels, replicated by one broadcast over NVLink
     res, idx, total = hmrt.pyramid_layout(COARSE, LEVELS)
@@ -273,10 +285,10 @@ def run_gpu_arm(args):
             dist.barrier()
 
     # ---- value: inputs resident, device-timed --------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None  # samples under load: warm-up + timed steps do the same work
     for s in range(args.warmup):
         ctx.trace(W, H, cams_by_step[s], opts, out=fb)
     barrier()
+    t_begin = time.time()
     launches0 = ctx.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -286,7 +298,8 @@ def run_gpu_arm(args):
     barrier()
     launches = ctx.launch_count - launches0
     ms = start.elapsed_time(stop)
-    clocks = sampler.stop() if sampler else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -333,9 +346,9 @@ def run_gpu_arm(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": rays_per_step * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 64,
+    e2e = {"value": rays_per_step * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 36,
            "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "note": "hmrt_trace_host: per-step camera constants H2D + whole-job RGB8 framebuffers D2H into pinned host memory; heightmap resident"}
+           "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory, copy of frame f overlapped with the traversal of frame f+1; heightmap resident"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's own code on the host cores ----------
     cpu = None
@@ -366,7 +379,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -81,7 +81,17 @@ int hmrt_destroy(hmrt_ctx* ctx) {
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (ctx->d_frames) cudaFree(ctx->d_frames);
   if (ctx->d_fb) cudaFree(ctx->d_fb);
-  if (ctx->d_hmax) cudaFree(ctx->d_hmax);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaStreamSynchronize(ctx->frame_stream[i]);
+      cudaEventDestroy(ctx->frame_event[i]);
+      cudaStreamDestroy(ctx->frame_stream[i]);
+    }
+    cudaEventDestroy(ctx->prep_event);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   delete ctx;
   return (int)e;
 }

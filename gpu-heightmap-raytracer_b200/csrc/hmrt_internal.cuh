@@ -29,13 +29,20 @@ struct hmrt_ctx {
   bool have_grid;
   hmrt::Grid grid;
   float init_max_height;
-  uint32_t* d_hmax; /* max(top level) as an ordered key, refreshed before every trace launch */
+  void* d_scratch;    /* TraceScratch[scratch_cap]: max(top level) key + one work counter per launch of a call */
+  int scratch_cap;
+  int ctas_per_sm[6]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;
   int frames_cap;
   /* context-owned framebuffer for hmrt_trace_host */
   uint8_t* d_fb;
   size_t fb_cap;
+  /* hmrt_trace_host: frames alternate between two streams, copies run on a third */
+  cudaStream_t copy_stream;
+  cudaStream_t frame_stream[2];
+  cudaEvent_t frame_event[2];
+  cudaEvent_t prep_event;
 };
 
 namespace hmrt {

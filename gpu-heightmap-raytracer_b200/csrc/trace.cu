@@ -6,13 +6,13 @@
  * 64-byte FrameConsts) and cuda_rayTrace (:195-222).
  *
  * Launch geometry (vs the reference's column-shaped block (1, H/2), :303-305, which is illegal
- * at H = 2160 and stores 3 bytes per thread with a stride of W*3):
- *   CTA  = 256 threads = 32 x 8 pixel tile; each warp owns an 8 x 4 pixel sub-tile so that
- *          the rays of a warp are neighbours in both image directions (coherent walks),
- *   grid = (ceil(W/32), local row tiles, frames): many frames (a fly-through, or a batch of
- *          camera poses) run in ONE launch,
- *   the 8 x 96-byte RGB rows of a tile are staged in shared memory and written with 128-bit
- *   stores (48 x 16 B per CTA) when W % 16 == 0, byte stores otherwise.
+ * at H = 2160 and stores 3 bytes per thread with a stride of W*3): a persistent grid of
+ * (SMs x resident CTAs) CTAs of 8 warps.  Every WARP repeatedly claims the next 32 x 4 pixel chunk
+ * of any frame of the launch from a global counter and walks it as four 8 x 4 pixel tiles, so the
+ * 32 rays in flight are neighbours in both image directions (coherent walks).  The chunk's
+ * 4 x 96 bytes of RGB8 are staged in the warp's private slice of shared memory and written with 24
+ * coalesced 128-bit stores (byte stores when W % 16 != 0 or on ragged edges).  Many frames
+ * (a fly-through, a batch of camera poses) run in ONE launch.
  */
 #include <string.h>
 
@@ -21,22 +21,35 @@
 
 namespace hmrt {
 
-constexpr int kTileW = 32;
-constexpr int kTileH = HMRT_ROW_TILE; /* 8 */
-constexpr int kThreads = kTileW * kTileH;
+constexpr int kThreads = 256; /* 8 warps per CTA */
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunkW = 32, kChunkH = 4; /* a warp's unit of work: four 8 x 4 pixel tiles side by side */
+constexpr int kStageRow = kChunkW * 3;   /* 96 bytes of RGB8 per chunk row */
+static_assert(HMRT_ROW_TILE == 2 * kChunkH, "a row tile is two chunk rows");
+
+/* device-side scratch refreshed by the launcher (16 bytes) */
+struct TraceScratch {
+  uint32_t hmax_key;             /* order-preserving key of max(top level), see top_level_max_kernel */
+  uint32_t pad;
+  unsigned long long next_chunk; /* work counter of the persistent kernel */
+};
 
 struct TraceParams {
   Grid grid;
   Shading shading;
-  FrameConsts frame0;        /* used when frames == nullptr (single-frame launch) */
-  const FrameConsts* frames; /* device array, one per blockIdx.z */
+  alignas(16) FrameConsts frame0; /* used when frames == nullptr (single-frame launch); read as 4 x float4 */
+  const FrameConsts* frames; /* device array, one per frame */
   uint8_t* rgb;
   hmrt_hit* hits;
   int W, H;
   int rows_local;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
-  const uint32_t* hmax_key; /* order-preserving key of max(top level), written by top_level_max_kernel */
+  const uint32_t* hmax_key;          /* &scratch[0].hmax_key */
+  unsigned long long* next_chunk;    /* this launch's work counter */
+  uint32_t chunks_x;               /* ceil(W / 32) */
+  uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
+  unsigned long long total_chunks; /* frames * chunks_per_frame */
 };
 
 /* float <-> unsigned key with the same ordering (so an unsigned atomicMax is a float max) */
@@ -49,7 +62,7 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 
 /*
- * Maximum of the coarsest pyramid level, recomputed before every trace launch because the
+ * Maximum of the coarsest pyramid level, recomputed before every trace call because the
  * heightmap buffer is borrowed and may have been refilled by the caller (the reference re-uploads
  * it every frame, main.cpp:623).  16 K floats for a 16384^2 map: a few microseconds.
  * A NaN cell yields a NaN maximum, which simply disables the air phase.
@@ -65,10 +78,17 @@ __global__ void __launch_bounds__(256) top_level_max_kernel(const float* __restr
  * (ray_core.cuh), kept as the in-library parity reference (hmrt_set_trace_variant). */
 enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2 };
 
+/*
+ * Persistent traversal kernel (see the file header).  There is no CTA-wide barrier after the
+ * prologue: a warp that finishes a cheap (sky) chunk immediately claims the next one instead of
+ * idling at a tile barrier (ncu r01: 17 % of the resident warps were parked at the barrier of the
+ * former one-tile-per-CTA kernel).
+ */
 template <bool HITS, int WALK>
-__global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p) {
-  __shared__ __align__(16) uint8_t stage[kTileH][kTileW * 3];
+__global__ void __launch_bounds__(kThreads) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
+  __shared__ __align__(16) uint8_t stage[kWarps][kChunkH][kStageRow];
   __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
+  __shared__ __align__(16) FrameConsts frame_s[kWarps]; /* the frame constants of each warp's current chunk */
   uint32_t tab = 0; /* shared-window address of the level table, pinned in a register */
   float hmax = 0.0f;
   if (WALK != kWalkReference) {
@@ -80,86 +100,137 @@ __global__ void __launch_bounds__(kThreads) trace_tiles_kernel(const __grid_cons
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  /* warp (wx, wy) in a 4 x 2 arrangement; lane (lx, ly) in an 8 x 4 arrangement */
-  const int tx = (warp & 3) * 8 + (lane & 7);
-  const int ty = (warp >> 2) * 4 + (lane >> 3);
-  const int px = blockIdx.x * kTileW + tx;
-  const int tile = p.tile_first + blockIdx.y * p.tile_stride;
-  const int py = tile * kTileH + ty;                 /* row in the frame */
-  const int row_local = blockIdx.y * kTileH + ty;    /* row in this call's output */
+  const int lx = lane & 7, ly = lane >> 3; /* 8 x 4 lanes */
   const size_t frame_px = (size_t)p.rows_local * (size_t)p.W;
-  const size_t frame_base = (size_t)blockIdx.z * frame_px;
 
-  const bool inside = px < p.W && py < p.H;
-  if (inside) {
-    FrameConsts f;
-    if (p.frames) {
-      const float4* src = reinterpret_cast<const float4*>(p.frames + blockIdx.z);
-      float4* dst = reinterpret_cast<float4*>(&f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+  for (;;) {
+    unsigned long long chunk = 0;
+    if (lane == 0) chunk = atomicAdd(p.next_chunk, 1ull);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= p.total_chunks) break;
+    /* chunk -> (frame, local row tile j, 4-row half, 32-pixel column group); consecutive chunks are
+     * neighbours along x, so concurrently running warps cover a compact band of the frame */
+    const uint32_t frame = (uint32_t)(chunk / p.chunks_per_frame);
+    const uint32_t in_frame = (uint32_t)(chunk - (unsigned long long)frame * p.chunks_per_frame);
+    const uint32_t strip = in_frame / p.chunks_x, cx = in_frame - strip * p.chunks_x;
+    const int j = (int)(strip >> 1), half = (int)(strip & 1u);
+    const int tile = p.tile_first + j * p.tile_stride;         /* 8-row tile in the frame */
+    const int row0 = tile * HMRT_ROW_TILE + half * kChunkH;    /* first row of the chunk in the frame */
+    const int row0_local = j * HMRT_ROW_TILE + half * kChunkH; /* ... in this call's output */
+    const int py = row0 + ly;
+    const int x0 = (int)cx * kChunkW;
+    const size_t frame_base = (size_t)frame * frame_px;
+
+    /* frame constants -> the warp's shared slot (read back at the start of every ray; keeping the 16
+     * floats in registers across the walk costs a whole CTA of occupancy) */
+    if (lane < 4) {
+      const float4* src = p.frames ? reinterpret_cast<const float4*>(p.frames + frame) : reinterpret_cast<const float4*>(&p.frame0);
+      reinterpret_cast<float4*>(&frame_s[warp])[lane] = src[lane];
+    }
+    __syncwarp();
+    const FrameConsts& f = frame_s[warp];
+
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) { /* the four 8 x 4 tiles of the chunk */
+      const int tx = k * 8 + lx;
+      const int px = x0 + tx;
+      if (px < p.W && py < p.H) {
+        RayResult r;
+        if (WALK == kWalkFastPow2)
+          r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+        else if (WALK == kWalkFast)
+          r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+        else
+          r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
+        stage[warp][ly][tx * 3 + 0] = r.r;
+        stage[warp][ly][tx * 3 + 1] = r.g;
+        stage[warp][ly][tx * 3 + 2] = r.b;
+        if (HITS)
+          reinterpret_cast<float4*>(p.hits)[frame_base + (size_t)(row0_local + ly) * p.W + px] =
+              make_float4(r.pos.x, r.pos.y, r.pos.z, __uint_as_float(r.flags));
+      }
+    }
+    __syncwarp();
+
+    uint8_t* out = p.rgb + frame_base * 3;
+    const bool full = (x0 + kChunkW <= p.W) && (row0 + kChunkH <= p.H);
+    if (p.vec_store && full) {
+      /* 4 rows x 6 pieces of 16 B; (x0 * 3) % 16 == 0 because x0 is a multiple of 32 */
+      if (lane < kChunkH * 6) {
+        const int r = lane / 6, c = lane % 6;
+        const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][r][c * 16]);
+        *reinterpret_cast<uint4*>(out + ((size_t)(row0_local + r) * p.W + x0) * 3 + c * 16) = v;
+      }
     } else {
-      f = p.frame0;
+      const int valid_w = min(kChunkW, p.W - x0), valid_h = min(kChunkH, p.H - row0);
+      for (int i = lane; i < kChunkH * kStageRow; i += 32) {
+        const int r = i / kStageRow, b = i % kStageRow;
+        if (r < valid_h && b < valid_w * 3) out[((size_t)(row0_local + r) * p.W + x0) * 3 + b] = stage[warp][r][b];
+      }
     }
-    RayResult r;
-    if (WALK == kWalkFastPow2)
-      r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
-    else if (WALK == kWalkFast)
-      r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
-    else
-      r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
-    stage[ty][tx * 3 + 0] = r.r;
-    stage[ty][tx * 3 + 1] = r.g;
-    stage[ty][tx * 3 + 2] = r.b;
-    if (HITS) {
-      hmrt_hit h;
-      h.x = r.pos.x;
-      h.y = r.pos.y;
-      h.z = r.pos.z;
-      h.flags = r.flags;
-      reinterpret_cast<float4*>(p.hits)[frame_base + (size_t)row_local * p.W + px] =
-          make_float4(h.x, h.y, h.z, __uint_as_float(h.flags));
-    }
-  }
-  __syncthreads();
-
-  uint8_t* out = p.rgb + frame_base * 3;
-  const int x0 = blockIdx.x * kTileW;
-  const bool full = (x0 + kTileW <= p.W) && (tile * kTileH + kTileH <= p.H);
-  if (p.vec_store && full) {
-    /* 8 rows x 6 chunks of 16 B; (x0*3) % 16 == 0 because x0 is a multiple of 32 */
-    if (threadIdx.x < kTileH * 6) {
-      const int r = threadIdx.x / 6, c = threadIdx.x % 6;
-      const uint4 v = *reinterpret_cast<const uint4*>(&stage[r][c * 16]);
-      uint8_t* dst = out + ((size_t)(blockIdx.y * kTileH + r) * p.W + x0) * 3 + c * 16;
-      *reinterpret_cast<uint4*>(dst) = v;
-    }
-  } else {
-    const int valid_w = min(kTileW, p.W - x0);
-    const int valid_h = min(kTileH, p.H - tile * kTileH);
-    for (int i = threadIdx.x; i < kTileH * kTileW * 3; i += kThreads) {
-      const int r = i / (kTileW * 3), b = i % (kTileW * 3);
-      if (r < valid_h && b < valid_w * 3)
-        out[((size_t)(blockIdx.y * kTileH + r) * p.W + x0) * 3 + b] = stage[r][b];
-    }
+    __syncwarp(); /* the stage slice is reused by the next chunk */
   }
 }
 
-static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, int n_frames,
-                        const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
+static const void* pick_kernel(bool hits, int walk) {
+#define HMRT_PICK(HITS_, WALK_) return reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_>)
+  if (hits) {
+    if (walk == kWalkFastPow2) HMRT_PICK(true, kWalkFastPow2);
+    if (walk == kWalkFast) HMRT_PICK(true, kWalkFast);
+    HMRT_PICK(true, kWalkReference);
+  }
+  if (walk == kWalkFastPow2) HMRT_PICK(false, kWalkFastPow2);
+  if (walk == kWalkFast) HMRT_PICK(false, kWalkFast);
+  HMRT_PICK(false, kWalkReference);
+#undef HMRT_PICK
+}
+
+/* Scratch slots: slot 0 also holds the top-level maximum; every launch of a call uses its own counter. */
+static int ensure_scratch(hmrt_ctx* ctx, int slots) {
+  if (ctx->scratch_cap >= slots) return 0;
+  if (ctx->d_scratch) HMRT_CUDA(cudaFree(ctx->d_scratch));
+  ctx->d_scratch = nullptr;
+  ctx->scratch_cap = 0;
+  HMRT_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(TraceScratch) * (size_t)slots));
+  ctx->scratch_cap = slots;
+  return 0;
+}
+
+/* Zero `slots` counters and refresh the top-level maximum, on the context's stream. */
+static int prepare_trace(hmrt_ctx* ctx, int slots) {
+  int rc = ensure_scratch(ctx, slots);
+  if (rc) return rc;
+  TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
+  HMRT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(TraceScratch) * (size_t)slots, ctx->stream));
+  if (ctx->trace_variant == 0) {
+    const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
+    const unsigned blocks = (unsigned)((n_top + 4095u) / 4096u);
+    top_level_max_kernel<<<blocks > 1184u ? 1184u : blocks, 256, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, &scratch->hmax_key);
+    HMRT_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+static int check_trace_args(const hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, int n_frames,
+                            const hmrt_trace_opts* opts) {
   if (!ctx || !cams || !opts) return HMRT_E_ARG;
   if (!ctx->have_grid) return HMRT_E_STATE;
   if (W < 2 || H < 2 || n_frames < 1 || n_frames > 65535) return HMRT_E_ARG;
   if (opts->use_color_map && !ctx->grid.color_map) return HMRT_E_ARG;
   if (opts->tile_first < 0 || opts->tile_stride < 0) return HMRT_E_ARG;
+  return 0;
+}
+
+/* One persistent launch over n_frames cameras on `stream`, using scratch slot `slot` as its counter
+ * (prepare_trace must have run on the context's stream and be ordered before `stream`). */
+static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int W, int H, const hmrt_camera* cams, int n_frames,
+                        const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
-  const int n_tiles = (H + kTileH - 1) / kTileH;
+  const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
   if (!d_rgb) return HMRT_E_ARG;
   const int local_tiles = (n_tiles - opts->tile_first + stride - 1) / stride;
-  if (local_tiles > 65535) return HMRT_E_SHAPE;
 
-  DeviceGuard guard(ctx->device);
   TraceParams p;
   memset(&p, 0, sizeof(p));
   p.grid = ctx->grid;
@@ -176,6 +247,12 @@ static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, in
   p.tile_first = opts->tile_first;
   p.tile_stride = stride;
   p.vec_store = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0);
+  p.chunks_x = (uint32_t)((W + kChunkW - 1) / kChunkW);
+  p.chunks_per_frame = (uint32_t)local_tiles * 2u * p.chunks_x;
+  p.total_chunks = (unsigned long long)p.chunks_per_frame * (unsigned long long)n_frames;
+  TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
+  p.hmax_key = &scratch[0].hmax_key;
+  p.next_chunk = &scratch[slot].next_chunk;
 
   if (n_frames == 1) {
     make_frame_consts(cams[0], p.frame0);
@@ -193,35 +270,26 @@ static int launch_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* cams, in
     for (int base = 0; base < n_frames; base += 64) {
       const int n = n_frames - base < 64 ? n_frames - base : 64;
       for (int i = 0; i < n; ++i) make_frame_consts(cams[base + i], local[i]);
-      HMRT_CUDA(cudaMemcpyAsync(ctx->d_frames + base, local, sizeof(FrameConsts) * (size_t)n,
-                                cudaMemcpyHostToDevice, ctx->stream));
+      HMRT_CUDA(cudaMemcpyAsync(ctx->d_frames + base, local, sizeof(FrameConsts) * (size_t)n, cudaMemcpyHostToDevice, stream));
     }
     p.frames = ctx->d_frames;
   }
 
-  const dim3 grid((W + kTileW - 1) / kTileW, local_tiles, n_frames);
   const bool pow2 = (ctx->grid.coarse_res & (ctx->grid.coarse_res - 1)) == 0;
   const int walk = ctx->trace_variant != 0 ? kWalkReference : (pow2 ? kWalkFastPow2 : kWalkFast);
-  if (walk != kWalkReference) {
-    if (!ctx->d_hmax) HMRT_CUDA(cudaMalloc(&ctx->d_hmax, sizeof(uint32_t)));
-    HMRT_CUDA(cudaMemsetAsync(ctx->d_hmax, 0, sizeof(uint32_t), ctx->stream));
-    const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
-    const unsigned blocks = (unsigned)((n_top + 4095u) / 4096u);
-    top_level_max_kernel<<<blocks > 1184u ? 1184u : blocks, 256, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, ctx->d_hmax);
-    HMRT_LAUNCHED(ctx);
-    p.hmax_key = ctx->d_hmax;
+  /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
+  const void* fn = pick_kernel(d_hits != nullptr, walk);
+  const int kslot = (d_hits ? 3 : 0) + walk;
+  if (ctx->ctas_per_sm[kslot] == 0) {
+    int per_sm = 0;
+    HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    ctx->ctas_per_sm[kslot] = per_sm < 1 ? 1 : per_sm;
   }
-#define HMRT_LAUNCH_TRACE(HITS_, WALK_) trace_tiles_kernel<HITS_, WALK_><<<grid, kThreads, 0, ctx->stream>>>(p)
-  if (d_hits) {
-    if (walk == kWalkFastPow2) HMRT_LAUNCH_TRACE(true, kWalkFastPow2);
-    else if (walk == kWalkFast) HMRT_LAUNCH_TRACE(true, kWalkFast);
-    else HMRT_LAUNCH_TRACE(true, kWalkReference);
-  } else {
-    if (walk == kWalkFastPow2) HMRT_LAUNCH_TRACE(false, kWalkFastPow2);
-    else if (walk == kWalkFast) HMRT_LAUNCH_TRACE(false, kWalkFast);
-    else HMRT_LAUNCH_TRACE(false, kWalkReference);
-  }
-#undef HMRT_LAUNCH_TRACE
+  const unsigned long long want = (p.total_chunks + kWarps - 1) / kWarps;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  void* args[] = {&p};
+  HMRT_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
   HMRT_LAUNCHED(ctx);
   return 0;
 }
@@ -232,15 +300,23 @@ extern "C" {
 
 int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
                const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
-  return hmrt::launch_trace(ctx, W, H, h_cameras, n_frames, opts, d_rgb, d_hits);
+  int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
+  if (rc) return rc;
+  hmrt::DeviceGuard guard(ctx->device);
+  rc = hmrt::prepare_trace(ctx, 1);
+  if (rc) return rc;
+  return hmrt::launch_trace(ctx, ctx->stream, 0, W, H, h_cameras, n_frames, opts, d_rgb, d_hits);
 }
 
 int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
                     const hmrt_trace_opts* opts, uint8_t* h_rgb) {
-  if (!ctx || !opts || !h_rgb || W < 2 || H < 2 || n_frames < 1) return HMRT_E_ARG;
+  int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
+  if (rc) return rc;
+  if (!h_rgb) return HMRT_E_ARG;
   hmrt::DeviceGuard guard(ctx->device);
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
-  const size_t bytes = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W * 3 * (size_t)n_frames;
+  const size_t frame_bytes = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W * 3;
+  const size_t bytes = frame_bytes * (size_t)n_frames;
   if (bytes == 0) return 0;
   if (ctx->fb_cap < bytes) {
     if (ctx->d_fb) HMRT_CUDA(cudaFree(ctx->d_fb));
@@ -249,10 +325,35 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
     HMRT_CUDA(cudaMalloc(&ctx->d_fb, bytes));
     ctx->fb_cap = bytes;
   }
-  int rc = hmrt::launch_trace(ctx, W, H, h_cameras, n_frames, opts, ctx->d_fb, nullptr);
+  if (!ctx->copy_stream) {
+    HMRT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      HMRT_CUDA(cudaStreamCreateWithFlags(&ctx->frame_stream[i], cudaStreamNonBlocking));
+      HMRT_CUDA(cudaEventCreateWithFlags(&ctx->frame_event[i], cudaEventDisableTiming));
+    }
+    HMRT_CUDA(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
+  }
+  /*
+   * One launch per frame, alternating between two internal streams so that the tail of frame f
+   * overlaps the head of frame f+1, each followed by its device->host copy on a third stream: the
+   * copy of frame f overlaps the traversal of the following frames (the reference serialises
+   * upload, trace and GL read-back every frame, main.cpp:947-966).  The top-level maximum is
+   * refreshed once per call on the context's stream; everything is ordered after prior work on it.
+   */
+  rc = hmrt::prepare_trace(ctx, n_frames);
   if (rc) return rc;
-  HMRT_CUDA(cudaMemcpyAsync(h_rgb, ctx->d_fb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  HMRT_CUDA(cudaStreamSynchronize(ctx->stream));
+  HMRT_CUDA(cudaEventRecord(ctx->prep_event, ctx->stream));
+  for (int i = 0; i < 2; ++i) HMRT_CUDA(cudaStreamWaitEvent(ctx->frame_stream[i], ctx->prep_event, 0));
+  for (int f = 0; f < n_frames; ++f) {
+    cudaStream_t st = ctx->frame_stream[f & 1];
+    rc = hmrt::launch_trace(ctx, st, f, W, H, h_cameras + f, 1, opts, ctx->d_fb + (size_t)f * frame_bytes, nullptr);
+    if (rc) return rc;
+    HMRT_CUDA(cudaEventRecord(ctx->frame_event[f & 1], st));
+    HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[f & 1], 0));
+    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f * frame_bytes, ctx->d_fb + (size_t)f * frame_bytes, frame_bytes,
+                              cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  HMRT_CUDA(cudaStreamSynchronize(ctx->copy_stream)); /* all frames traced and copied */
   return 0;
 }
 
