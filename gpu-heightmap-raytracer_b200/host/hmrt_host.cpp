@@ -1,0 +1,414 @@
+/* hmrt_host.cpp -- see hmrt_host.hpp.  Host logic only; every computation on the traced /
+ * rasterised path happens in libhmrt.so's CUDA kernels. */
+#include "hmrt_host.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+namespace hmrt_host {
+
+/* ---------------------------------------------------------------------------------------------- */
+PyramidLayout::PyramidLayout(int coarse, int lv) : coarse_res(coarse), levels(lv) {
+  if (lv < 1 || lv > HMRT_MAX_LEVELS) return;
+  res.assign(lv, 0);
+  idx.assign(lv, 0);
+  if (hmrt_pyramid_layout(coarse, lv, res.data(), idx.data(), &total) != 0) {
+    res.clear();
+    idx.clear();
+    total = 0;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+static uint16_t rd_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static uint32_t rd_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static double rd_f64(const uint8_t* p) {
+  double d;
+  std::memcpy(&d, p, 8);
+  return d;
+}
+
+bool LasFile::open(const std::string& path, LasFile& out, std::string* error) {
+  auto fail = [&](const char* why) {
+    if (error) *error = why;
+    return false;
+  };
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return fail("cannot open file");
+  uint8_t h[227];
+  if (!f.read(reinterpret_cast<char*>(h), sizeof h)) return fail("short LAS header");
+  if (std::memcmp(h, "LASF", 4) != 0) return fail("not a LAS file");
+  if (h[104] & 0xC0) return fail("compressed (LAZ) point data is not supported");
+  out.point_format = h[104] & 0x3F;
+  static const int min_len[4] = {20, 28, 26, 34};
+  if (out.point_format > 3) return fail("unsupported point data format (0-3 supported)");
+  out.record_len = rd_u16(h + 105);
+  if (out.record_len < min_len[out.point_format]) return fail("record length shorter than the point format");
+  out.offset_to_points = rd_u32(h + 96);
+  out.n_points = rd_u32(h + 107);
+  for (int i = 0; i < 3; ++i) {
+    out.scale[i] = rd_f64(h + 131 + 8 * i);
+    out.offset[i] = rd_f64(h + 155 + 8 * i);
+    out.max[i] = rd_f64(h + 179 + 16 * i);
+    out.min[i] = rd_f64(h + 187 + 16 * i);
+  }
+  out.path = path;
+  return true;
+}
+
+bool LasFile::read_records(uint64_t first, uint64_t count, uint8_t* dst) const {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  f.seekg((std::streamoff)offset_to_points + (std::streamoff)(first * (uint64_t)record_len));
+  return (bool)f.read(reinterpret_cast<char*>(dst), (std::streamsize)(count * (uint64_t)record_len));
+}
+
+bool LasFile::first_point(double xyz[3]) const {
+  if (n_points == 0) return false;
+  std::vector<uint8_t> rec(record_len);
+  if (!read_records(0, 1, rec.data())) return false;
+  for (int i = 0; i < 3; ++i) xyz[i] = (double)(int32_t)rd_u32(rec.data() + 4 * i) * scale[i] + offset[i]; /* libLAS GetX() */
+  return true;
+}
+
+hmrt_las_transform LasFile::transform(const float cell_size[3], const float origin[2]) const {
+  hmrt_las_transform t;
+  for (int i = 0; i < 3; ++i) {
+    t.scale[i] = scale[i];
+    t.offset[i] = offset[i];
+    t.min[i] = min[i];
+    t.cell_size[i] = cell_size[i];
+  }
+  t.origin[0] = origin[0];
+  t.origin[1] = origin[1];
+  return t;
+}
+
+SceneInfo read_las_header(const LasFile& las) { /* main.cpp:153-164 */
+  SceneInfo s;
+  const double dX = las.max[0] - las.min[0], dY = las.max[1] - las.min[1];
+  s.boundaries[0] = (float)(dX / s.cell_size[0]);
+  s.boundaries[1] = (float)(dY / s.cell_size[1]);
+  double p[3];
+  if (las.first_point(p)) {
+    s.camera_position.x = (float)((p[0] - las.min[0]) / s.cell_size[0]);
+    s.camera_position.y = (float)((las.max[2] - las.min[2]) / s.cell_size[2]);
+    s.camera_position.z = (float)((p[1] - las.min[1]) / s.cell_size[0]);
+  }
+  s.max_height = static_cast<float>(las.max[2] - las.min[2]) / s.cell_size[2];
+  return s;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* PointdataGenerator/main.cpp:72-184 with an explicit seed (64-bit LCG, top 24 bits -> [0,1)) */
+namespace {
+struct Lcg {
+  uint64_t s;
+  float next() {
+    s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+    return (float)(s >> 40) * (1.0f / 16777216.0f);
+  }
+};
+}  // namespace
+
+std::vector<float> pdg_generate(int n, uint64_t seed) {
+  const int G = n + 1;
+  if (n < 2 || (n & (n - 1))) return {};
+  std::vector<float> z((size_t)G * G, 0.f);
+  auto at = [&](int i, int j) -> float& { return z[(size_t)i * G + j]; };
+  Lcg gen{seed};
+  at(0, 0) = gen.next(); /* PDG:91-94 */
+  at(0, G - 1) = gen.next();
+  at(G - 1, 0) = gen.next();
+  at(G - 1, G - 1) = gen.next();
+  auto rough = [&](int count) { return (float)std::pow((double)gen.next(), (double)count); }; /* PDG:105 */
+  auto diamond = [&](int x, int y, int s, float r) {                                          /* PDG:117-130 */
+    at(x, y) = (at(x + s, y + s) + at(x - s, y + s) + at(x + s, y - s) + at(x - s, y - s)) / 4 + r;
+  };
+  auto square = [&](int x, int y, int s, float r) { /* PDG:132-158 */
+    float left = 0, right = 0, top = 0, bottom = 0;
+    int count = 0;
+    if (x > 0) left = at(x - s, y), count++;
+    if (x < G - 1) right = at(x + s, y), count++;
+    if (y > 0) top = at(x, y - s), count++;
+    if (y < G - 1) bottom = at(x, y + s), count++;
+    at(x, y) = (left + right + top + bottom) / count + r;
+  };
+  int count = 1;
+  for (int i = G; i > 1; i /= 2) { /* PDG:100-112 */
+    for (int x = i / 2; x < G; x += i)
+      for (int y = i / 2; y < G; y += i) {
+        float r = rough(count);
+        diamond(x, y, i / 2, r);
+        r = rough(count);
+        square(x, y - i / 2, i / 2, r);
+        r = rough(count);
+        square(x - i / 2, y, i / 2, r);
+        r = rough(count);
+        square(x + i / 2, y, i / 2, r);
+        r = rough(count);
+        square(x, y + i / 2, i / 2, r);
+      }
+    ++count;
+  }
+  for (int i = 0; i < G - 1; ++i) /* scaleData, PDG:175-184 */
+    for (int j = 0; j < G - 1; ++j) at(i, j) *= 10.f;
+  std::vector<float> xyz((size_t)G * G * 3);
+  for (int i = 0; i < G; ++i)
+    for (int j = 0; j < G; ++j) {
+      const size_t k = ((size_t)i * G + j) * 3;
+      xyz[k] = (float)i, xyz[k + 1] = (float)j, xyz[k + 2] = at(i, j);
+    }
+  return xyz;
+}
+
+bool write_pdg_text(const std::string& path, const std::vector<float>& xyz) {
+  FILE* f = std::fopen(path.c_str(), "w");
+  if (!f) return false;
+  for (size_t i = 0; i + 2 < xyz.size(); i += 3) std::fprintf(f, "%.7f %.7f %.7f\n", xyz[i], xyz[i + 1], xyz[i + 2]);
+  return std::fclose(f) == 0;
+}
+
+bool read_pdg_text(const std::string& path, std::vector<float>& xyz) {
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) return false;
+  xyz.clear();
+  float x, y, z;
+  while (std::fscanf(f, "%f %f %f", &x, &y, &z) == 3) {
+    xyz.push_back(x);
+    xyz.push_back(y);
+    xyz.push_back(z);
+  }
+  std::fclose(f);
+  return !xyz.empty();
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+Heightmap::Heightmap(hmrt_ctx* ctx, int coarse_res, int levels, bool with_colors) : ctx_(ctx), layout_(coarse_res, levels) {
+  if (layout_.total == 0) {
+    status_ = HMRT_E_SHAPE;
+    return;
+  }
+  const size_t cells = (size_t)layout_.finest() * layout_.finest();
+  status_ = (int)cudaMalloc(&d_pyramid_, sizeof(float) * (size_t)layout_.total); /* main.cpp:1012 */
+  if (status_ == 0 && with_colors) {
+    status_ = (int)cudaMalloc(&d_color_map_, 3 * cells); /* main.cpp:1013 */
+    if (status_ == 0) status_ = (int)cudaMalloc(&d_color_keys_, sizeof(uint64_t) * cells);
+  }
+  if (status_ == 0) status_ = clear();
+}
+
+Heightmap::~Heightmap() {
+  cudaFree(d_pyramid_);
+  cudaFree(d_color_map_);
+  cudaFree(d_color_keys_);
+}
+
+int Heightmap::clear() {
+  points_seen_ = 0;
+  return hmrt_clear_section(ctx_, d_pyramid_, layout_.coarse_res, layout_.levels, d_color_keys_, d_color_map_);
+}
+
+int Heightmap::rasterise_las(const LasFile& las, const float cell_size[3], const float origin[2], uint64_t chunk_points) {
+  const hmrt_las_transform xf = las.transform(cell_size, origin);
+  const size_t chunk_bytes = (size_t)chunk_points * las.record_len;
+  uint8_t* h_buf[2] = {nullptr, nullptr};
+  uint8_t* d_buf[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  int rc = 0;
+  for (int i = 0; i < 2 && rc == 0; ++i) { /* double-buffered pinned staging */
+    rc = (int)cudaMallocHost(&h_buf[i], chunk_bytes);
+    if (rc == 0) rc = (int)cudaMalloc(&d_buf[i], chunk_bytes);
+    if (rc == 0) rc = (int)cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+  }
+  uint64_t first = 0;
+  for (int k = 0; rc == 0 && first < las.n_points; ++k) {
+    const int b = k & 1;
+    const uint64_t n = std::min<uint64_t>(chunk_points, las.n_points - first);
+    if (k >= 2) rc = (int)cudaEventSynchronize(done[b]); /* buffer b is free again */
+    if (rc == 0 && !las.read_records(first, n, h_buf[b])) rc = HMRT_E_ARG;
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_buf[b], h_buf[b], (size_t)n * las.record_len, cudaMemcpyHostToDevice, 0);
+    if (rc == 0)
+      rc = hmrt_scatter_las(ctx_, d_buf[b], (int64_t)n, las.record_len, las.point_format, &xf, (int64_t)(points_seen_ + first),
+                            d_pyramid_, layout_.coarse_res, layout_.levels, d_color_keys_);
+    if (rc == 0) rc = (int)cudaEventRecord(done[b], 0);
+    first += n;
+  }
+  if (rc == 0) rc = hmrt_synchronize(ctx_);
+  points_seen_ += las.n_points;
+  for (int i = 0; i < 2; ++i) {
+    if (h_buf[i]) cudaFreeHost(h_buf[i]);
+    if (d_buf[i]) cudaFree(d_buf[i]);
+  }
+  return rc;
+}
+
+int Heightmap::rasterise_xyz(const std::vector<float>& xyz, const float cell_size[3], const float origin[2]) {
+  hmrt_las_transform xf;
+  for (int i = 0; i < 3; ++i) {
+    xf.scale[i] = 1.0;
+    xf.offset[i] = 0.0;
+    xf.min[i] = 0.0;
+    xf.cell_size[i] = cell_size[i];
+  }
+  xf.origin[0] = origin[0];
+  xf.origin[1] = origin[1];
+  const int64_t n = (int64_t)(xyz.size() / 3);
+  float* d = nullptr;
+  int rc = (int)cudaMalloc(&d, sizeof(float) * xyz.size());
+  if (rc == 0) rc = (int)cudaMemcpy(d, xyz.data(), sizeof(float) * xyz.size(), cudaMemcpyHostToDevice);
+  if (rc == 0) rc = hmrt_scatter_xyz(ctx_, d, n, &xf, d_pyramid_, layout_.coarse_res, layout_.levels);
+  if (rc == 0) rc = hmrt_synchronize(ctx_);
+  cudaFree(d);
+  return rc;
+}
+
+int Heightmap::finish() {
+  int rc = hmrt_build_mips(ctx_, d_pyramid_, layout_.coarse_res, layout_.levels);
+  if (rc == 0 && d_color_keys_)
+    rc = hmrt_resolve_colors(ctx_, d_color_keys_, d_color_map_, (int64_t)layout_.finest() * layout_.finest());
+  if (rc == 0) rc = hmrt_synchronize(ctx_);
+  return rc;
+}
+
+int Heightmap::max_height(float* out) const {
+  const size_t n = (size_t)layout_.coarse_res * layout_.coarse_res;
+  std::vector<float> top(n);
+  int rc = (int)cudaMemcpy(top.data(), d_pyramid_, n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (rc == 0) *out = *std::max_element(top.begin(), top.end());
+  return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+static Vec3 normalize(Vec3 v) {
+  const float s = 1.0f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  return {v.x * s, v.y * s, v.z * s};
+}
+static Vec3 cross(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+/* glm::rotate(v, angle, axis) (gtx/rotate_vector): Rodrigues' formula */
+static Vec3 rotate(Vec3 v, float angle, Vec3 k) {
+  const float c = std::cos(angle), s = std::sin(angle);
+  const Vec3 kxv = cross(k, v);
+  const float kv = (k.x * v.x + k.y * v.y + k.z * v.z) * (1 - c);
+  return {v.x * c + kxv.x * s + k.x * kv, v.y * c + kxv.y * s + k.y * kv, v.z * c + kxv.z * s + k.z * kv};
+}
+
+void Camera::move(float fwd, float right, float up, float dt, const float boundaries[2], float max_height) {
+  const float factor = dt > 1 ? 1 : dt; /* main.cpp:755 */
+  const Vec3 f = normalize({forward.x, 0, forward.z});
+  const Vec3 r = normalize(cross(forward, {0, 1, 0}));
+  position.x += factor * (f.x * fwd + r.x * right);
+  position.y += factor * (up + f.y * fwd + r.y * right);
+  position.z += factor * (f.z * fwd + r.z * right);
+  if (position.x < 0) position.x = 0; /* main.cpp:758-771 */
+  if (position.x >= boundaries[0]) position.x = boundaries[0] - 0.00001f;
+  if (position.z < 0) position.z = 0;
+  if (position.z >= boundaries[1]) position.z = boundaries[1] - 0.00001f;
+  if (position.y < 0) position.y = 0;
+  if (position.y >= max_height * 4) position.y = max_height * 4;
+}
+
+void Camera::rotate(float yaw, float pitch, float dt) { /* main.cpp:779-780 */
+  forward = hmrt_host::rotate(forward, yaw * dt, {0, 1, 0});
+  forward = hmrt_host::rotate(forward, pitch * dt, normalize(cross(forward, {0, 1, 0})));
+}
+
+hmrt_camera Camera::abi() const {
+  hmrt_camera c;
+  c.frame_dim[0] = frame_dimension.x, c.frame_dim[1] = frame_dimension.y, c.frame_dim[2] = frame_dimension.z;
+  c.forward[0] = forward.x, c.forward[1] = forward.y, c.forward[2] = forward.z;
+  c.position[0] = position.x, c.position[1] = position.y, c.position[2] = position.z;
+  return c;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+Renderer::Renderer(hmrt_ctx* ctx, int width, int height) : ctx_(ctx), w_(width), h_(height) {
+  cudaMalloc(&d_rgb_, (size_t)width * height * 3); /* the PBO of main.cpp:642-645 */
+}
+Renderer::~Renderer() { cudaFree(d_rgb_); }
+
+int Renderer::set_heightmap(const Heightmap& hm, float max_height) {
+  return hmrt_set_heightmap(ctx_, hm.d_pyramid(), hm.d_color_map(), hm.layout().coarse_res, hm.layout().levels, max_height);
+}
+
+int Renderer::render(const Camera& cam, const hmrt_trace_opts& opts) {
+  if (!d_rgb_) return HMRT_E_NOMEM;
+  const hmrt_camera c = cam.abi();
+  int rc = hmrt_trace(ctx_, w_, h_, &c, 1, &opts, d_rgb_, nullptr);
+  if (rc == 0) rc = hmrt_synchronize(ctx_);
+  return rc;
+}
+
+int Renderer::render_to_host(const std::vector<Camera>& cams, const hmrt_trace_opts& opts, uint8_t* h_rgb) {
+  std::vector<hmrt_camera> c(cams.size());
+  for (size_t i = 0; i < cams.size(); ++i) c[i] = cams[i].abi();
+  return hmrt_trace_host(ctx_, w_, h_, c.data(), (int)c.size(), &opts, h_rgb);
+}
+
+int Renderer::download(std::vector<uint8_t>& rgb) const {
+  rgb.resize((size_t)w_ * h_ * 3);
+  return (int)cudaMemcpy(rgb.data(), d_rgb_, rgb.size(), cudaMemcpyDeviceToHost);
+}
+
+bool write_ppm(const std::string& path, const uint8_t* rgb, int width, int height, bool flip) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) return false;
+  std::fprintf(f, "P6\n%d %d\n255\n", width, height);
+  for (int y = 0; y < height; ++y) {
+    const int row = flip ? height - 1 - y : y;
+    std::fwrite(rgb + (size_t)row * width * 3, 1, (size_t)width * 3, f);
+  }
+  return std::fclose(f) == 0;
+}
+
+}  // namespace hmrt_host
+
+/* ---- plain-C views of the host helpers (used by the Python tests through ctypes) -------------- */
+extern "C" {
+
+int hmrt_host_pdg_generate(int n, uint64_t seed, float* out_xyz) {
+  const std::vector<float> v = hmrt_host::pdg_generate(n, seed);
+  if (v.empty()) return HMRT_E_ARG;
+  std::memcpy(out_xyz, v.data(), v.size() * sizeof(float));
+  return 0;
+}
+
+/* out[0..11] = scale xyz, offset xyz, min xyz, max xyz; meta = format, record_len, n_points, offset_to_points */
+int hmrt_host_las_info(const char* path, double* out, uint64_t* meta) {
+  hmrt_host::LasFile las;
+  if (!hmrt_host::LasFile::open(path, las)) return HMRT_E_ARG;
+  for (int i = 0; i < 3; ++i) out[i] = las.scale[i], out[3 + i] = las.offset[i], out[6 + i] = las.min[i], out[9 + i] = las.max[i];
+  meta[0] = (uint64_t)las.point_format, meta[1] = (uint64_t)las.record_len, meta[2] = las.n_points, meta[3] = las.offset_to_points;
+  return 0;
+}
+
+/* scene = cell_size xyz, boundaries xy, camera xyz, max_height (readLASHeader, main.cpp:153-164) */
+int hmrt_host_las_scene(const char* path, float* scene) {
+  hmrt_host::LasFile las;
+  if (!hmrt_host::LasFile::open(path, las)) return HMRT_E_ARG;
+  const hmrt_host::SceneInfo s = hmrt_host::read_las_header(las);
+  scene[0] = s.cell_size[0], scene[1] = s.cell_size[1], scene[2] = s.cell_size[2];
+  scene[3] = s.boundaries[0], scene[4] = s.boundaries[1];
+  scene[5] = s.camera_position.x, scene[6] = s.camera_position.y, scene[7] = s.camera_position.z;
+  scene[8] = s.max_height;
+  return 0;
+}
+
+/* camera motion rules: state = position xyz, forward xyz */
+void hmrt_host_camera_step(float* state, float fwd, float right, float up, float yaw, float pitch, float dt, const float* boundaries,
+                           float max_height) {
+  hmrt_host::Camera c;
+  c.position = {state[0], state[1], state[2]};
+  c.forward = {state[3], state[4], state[5]};
+  c.move(fwd, right, up, dt, boundaries, max_height);
+  c.rotate(yaw, pitch, dt);
+  state[0] = c.position.x, state[1] = c.position.y, state[2] = c.position.z;
+  state[3] = c.forward.x, state[4] = c.forward.y, state[5] = c.forward.z;
+}
+
+}  // extern "C"
