@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Rasterisation side of the hot path (BASELINE.json configs[3]): N synthetic LAS points -> 16384^2 grid.
+
+Reports Mpoints/s of the scatter kernel, GB/s of the max-mipmap build, their algorithmic-byte rooflines
+(scatter = n * (record_bytes + 4), mips = 4 * R0^2 * 4/3) and, under torchrun, the
+NCCL max all-reduce that combines the per-GPU partial heightmaps.  One JSON line on rank 0.
+
+  python benchmarks/raster_bench.py --points 500000000
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 benchmarks/raster_bench.py --points 500000000
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "gpu-heightmap-raytracer_b200"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import hmrt  # noqa: E402
+from hmrt import dist as hd  # noqa: E402
+from hmrt import las  # noqa: E402
+
+R0, LEVELS = 16384, 8
+COARSE = R0 >> (LEVELS - 1)
+
+
+def make_records(n, fmt, seed, order):
+    """n LAS records (format 0: 20 B, format 2: 26 B) on the device; 'random' = uniformly scattered points,
+    'swath' = points sorted by scan line (row-major cell order with jitter), like an airborne survey file."""
+    rec_len = las.RECORD_MIN_LEN[fmt]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ext_raw = int(R0 * 2.0 / 0.01)
+    X = torch.randint(0, ext_raw, (n,), device="cuda", generator=g, dtype=torch.int32)
+    if order == "swath":
+        Y = (torch.arange(n, device="cuda", dtype=torch.float64) * (ext_raw / n)).to(torch.int32)
+    else:
+        Y = torch.randint(0, ext_raw, (n,), device="cuda", generator=g, dtype=torch.int32)
+    Z = (40000 + 26000 * torch.sin(X.float() * 6e-6) * torch.cos(Y.float() * 5e-6)).to(torch.int32)
+    Z += torch.randint(0, 300, (n,), device="cuda", generator=g, dtype=torch.int32)
+    rec = torch.zeros((n, rec_len), dtype=torch.uint8, device="cuda")
+    rec[:, 0:4] = X.view(torch.uint8).view(n, 4)
+    rec[:, 4:8] = Y.view(torch.uint8).view(n, 4)
+    rec[:, 8:12] = Z.view(torch.uint8).view(n, 4)
+    del X, Y, Z
+    return rec, rec_len
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=500_000_000)
+    ap.add_argument("--format", type=int, default=0, choices=[0, 2])
+    ap.add_argument("--order", default="random", choices=["random", "swath"])
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = hmrt.Context(local)
+    res, idx, total = hmrt.pyramid_layout(COARSE, LEVELS)
+    lo, hi = hd.shard_range(args.points, rank, world)
+    n = hi - lo
+    rec, rec_len = make_records(n, args.format, 1000 + rank, args.order)
+    hdr = las.LasHeader(args.format, rec_len, args.points, (0.01, 0.01, 0.01), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (R0 * 2.0, R0 * 2.0, 700.0))
+    xf = hdr.transform()
+    pyr = torch.empty(total, dtype=torch.float32, device="cuda")
+    finest = pyr[idx[0]:]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    best = None
+    for _ in range(args.reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev[0].record()
+        ctx.clear_section(pyr, COARSE, LEVELS)
+        ev[1].record()
+        ctx.scatter_las(rec, n, rec_len, args.format, xf, pyr, COARSE, LEVELS, first_index=lo)
+        ev[2].record()
+        hd.allreduce_max_heights(finest)
+        ev[3].record()
+        ctx.build_mips(pyr, COARSE, LEVELS)
+        ev[4].record()
+        torch.cuda.synchronize()
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        if best is None or sum(t) < sum(best):
+            best = t
+    times = torch.tensor(best, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    clear_ms, scatter_ms, reduce_ms, mips_ms = [float(v) for v in times]
+    peak = 6550.7
+    pk = REPO / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = float(json.loads(pk.read_text())["hbm_gbs"])
+    scatter_bytes = n * (rec_len + 4)
+    mip_bytes = 4 * R0 * R0 * 4 / 3
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"{args.points} LAS format-{args.format} points ({args.order} order) -> {R0}^2 grid, {world} GPU(s)",
+            "scatter": {"ms": scatter_ms, "Mpoints_per_s_total": args.points / scatter_ms / 1e3, "algorithmic_GBps_per_gpu": scatter_bytes / scatter_ms / 1e6,
+                        "roofline_frac": scatter_bytes / scatter_ms / 1e6 / peak},
+            "mips": {"ms": mips_ms, "algorithmic_GBps": mip_bytes / mips_ms / 1e6, "roofline_frac": mip_bytes / mips_ms / 1e6 / peak},
+            "clear_ms": clear_ms, "allreduce_max_ms": reduce_ms if world > 1 else None,
+            "allreduce_busbw_GBps": (2 * (world - 1) / world * 4 * R0 * R0 / reduce_ms / 1e6) if world > 1 else None,
+            "end_to_end_ms": clear_ms + scatter_ms + reduce_ms + mips_ms,
+            "end_to_end_Mpoints_per_s": args.points / (clear_ms + scatter_ms + reduce_ms + mips_ms) / 1e3,
+            "hbm_peak_GBps": peak}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

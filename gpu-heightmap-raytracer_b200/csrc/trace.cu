@@ -223,8 +223,20 @@ static int check_trace_args(const hmrt_ctx* ctx, int W, int H, const hmrt_camera
 
 /* One persistent launch over n_frames cameras on `stream`, using scratch slot `slot` as its counter
  * (prepare_trace must have run on the context's stream and be ordered before `stream`). */
-static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int W, int H, const hmrt_camera* cams, int n_frames,
-                        const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
+static int ensure_frames(hmrt_ctx* ctx, int n) {
+  if (ctx->frames_cap >= n) return 0;
+  if (ctx->d_frames) HMRT_CUDA(cudaFree(ctx->d_frames)); /* cudaFree waits for in-flight work */
+  ctx->d_frames = nullptr;
+  ctx->frames_cap = 0;
+  HMRT_CUDA(cudaMalloc(&ctx->d_frames, sizeof(FrameConsts) * (size_t)n));
+  ctx->frames_cap = n;
+  return 0;
+}
+
+/* `frames_at`: index into ctx->d_frames where this launch keeps its per-frame constants (launches of
+ * one call that run on different streams must not share them). */
+static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
+                        int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
@@ -258,21 +270,17 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int W, int
     make_frame_consts(cams[0], p.frame0);
     p.frames = nullptr;
   } else {
-    if (ctx->frames_cap < n_frames) {
-      if (ctx->d_frames) HMRT_CUDA(cudaFree(ctx->d_frames));
-      ctx->d_frames = nullptr;
-      ctx->frames_cap = 0;
-      HMRT_CUDA(cudaMalloc(&ctx->d_frames, sizeof(FrameConsts) * (size_t)n_frames));
-      ctx->frames_cap = n_frames;
-    }
+    int rc = ensure_frames(ctx, frames_at + n_frames);
+    if (rc) return rc;
     /* pageable source: the runtime stages it before returning, so the stack buffer may die */
     FrameConsts local[64];
     for (int base = 0; base < n_frames; base += 64) {
       const int n = n_frames - base < 64 ? n_frames - base : 64;
       for (int i = 0; i < n; ++i) make_frame_consts(cams[base + i], local[i]);
-      HMRT_CUDA(cudaMemcpyAsync(ctx->d_frames + base, local, sizeof(FrameConsts) * (size_t)n, cudaMemcpyHostToDevice, stream));
+      HMRT_CUDA(cudaMemcpyAsync(ctx->d_frames + frames_at + base, local, sizeof(FrameConsts) * (size_t)n, cudaMemcpyHostToDevice,
+                                stream));
     }
-    p.frames = ctx->d_frames;
+    p.frames = ctx->d_frames + frames_at;
   }
 
   const bool pow2 = (ctx->grid.coarse_res & (ctx->grid.coarse_res - 1)) == 0;
@@ -305,7 +313,7 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
   hmrt::DeviceGuard guard(ctx->device);
   rc = hmrt::prepare_trace(ctx, 1);
   if (rc) return rc;
-  return hmrt::launch_trace(ctx, ctx->stream, 0, W, H, h_cameras, n_frames, opts, d_rgb, d_hits);
+  return hmrt::launch_trace(ctx, ctx->stream, 0, 0, W, H, h_cameras, n_frames, opts, d_rgb, d_hits);
 }
 
 int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
@@ -340,17 +348,27 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
    * upload, trace and GL read-back every frame, main.cpp:947-966).  The top-level maximum is
    * refreshed once per call on the context's stream; everything is ordered after prior work on it.
    */
-  rc = hmrt::prepare_trace(ctx, n_frames);
+  /* frames per launch: enough rays (>= ~4 M) to amortise launch + tail, e.g. 1 whole 4K frame on one
+   * GPU, 4 frames when a rank only owns 1/8 of every frame */
+  const size_t rays_per_frame = frame_bytes / 3;
+  int group = (int)((4000000 + rays_per_frame - 1) / rays_per_frame);
+  if (group < 1) group = 1;
+  if (group > n_frames) group = n_frames;
+  const int n_launches = (n_frames + group - 1) / group;
+  rc = hmrt::prepare_trace(ctx, n_launches);
+  if (rc) return rc;
+  rc = hmrt::ensure_frames(ctx, n_frames); /* sized up front: no reallocation while launches are in flight */
   if (rc) return rc;
   HMRT_CUDA(cudaEventRecord(ctx->prep_event, ctx->stream));
   for (int i = 0; i < 2; ++i) HMRT_CUDA(cudaStreamWaitEvent(ctx->frame_stream[i], ctx->prep_event, 0));
-  for (int f = 0; f < n_frames; ++f) {
-    cudaStream_t st = ctx->frame_stream[f & 1];
-    rc = hmrt::launch_trace(ctx, st, f, W, H, h_cameras + f, 1, opts, ctx->d_fb + (size_t)f * frame_bytes, nullptr);
+  for (int l = 0; l < n_launches; ++l) {
+    const int f0 = l * group, nf = (n_frames - f0 < group) ? n_frames - f0 : group;
+    cudaStream_t st = ctx->frame_stream[l & 1];
+    rc = hmrt::launch_trace(ctx, st, l, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr);
     if (rc) return rc;
-    HMRT_CUDA(cudaEventRecord(ctx->frame_event[f & 1], st));
-    HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[f & 1], 0));
-    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f * frame_bytes, ctx->d_fb + (size_t)f * frame_bytes, frame_bytes,
+    HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
+    HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
+    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f0 * frame_bytes, ctx->d_fb + (size_t)f0 * frame_bytes, frame_bytes * (size_t)nf,
                               cudaMemcpyDeviceToHost, ctx->copy_stream));
   }
   HMRT_CUDA(cudaStreamSynchronize(ctx->copy_stream)); /* all frames traced and copied */
