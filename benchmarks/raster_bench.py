@@ -55,12 +55,14 @@ def main():
     ap.add_argument("--format", type=int, default=0, choices=[0, 2])
     ap.add_argument("--order", default="random", choices=["random", "swath"])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 direct atomics, 2 tile-binned")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = hmrt.Context(local)
+    ctx.set_scatter_mode(args.mode)
     res, idx, total = hmrt.pyramid_layout(COARSE, LEVELS)
     lo, hi = hd.shard_range(args.points, rank, world)
     n = hi - lo
@@ -100,7 +102,7 @@ def main():
     mip_bytes = 4 * R0 * R0 * 4 / 3
     if rank == 0:
         print(json.dumps({
-            "workload": f"{args.points} LAS format-{args.format} points ({args.order} order) -> {R0}^2 grid, {world} GPU(s)",
+            "workload": f"{args.points} LAS format-{args.format} points ({args.order} order) -> {R0}^2 grid, {world} GPU(s), scatter mode {args.mode}",
             "scatter": {"ms": scatter_ms, "Mpoints_per_s_total": args.points / scatter_ms / 1e3, "algorithmic_GBps_per_gpu": scatter_bytes / scatter_ms / 1e6,
                         "roofline_frac": scatter_bytes / scatter_ms / 1e6 / peak},
             "mips": {"ms": mips_ms, "algorithmic_GBps": mip_bytes / mips_ms / 1e6, "roofline_frac": mip_bytes / mips_ms / 1e6 / peak},

@@ -82,6 +82,8 @@ int hmrt_destroy(hmrt_ctx* ctx) {
   if (ctx->d_frames) cudaFree(ctx->d_frames);
   if (ctx->d_fb) cudaFree(ctx->d_fb);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_ws) cudaFree(ctx->d_ws);
+  if (ctx->d_probe) cudaFree(ctx->d_probe);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2; ++i) {

@@ -25,6 +25,11 @@ struct hmrt_ctx {
   cudaStream_t stream;
   int64_t launches;
   int trace_variant; /* 0 = production walk, 1 = operation-by-operation walk (diagnostic) */
+  /* rasterisation: 0 = choose per call (locality probe), 1 = direct atomics, 2 = tile-binned */
+  int scatter_mode;
+  void* d_ws; /* bucket workspace of the binned scatter */
+  size_t ws_cap;
+  uint32_t* d_probe;
   /* borrowed heightmap (hmrt_set_heightmap) */
   bool have_grid;
   hmrt::Grid grid;

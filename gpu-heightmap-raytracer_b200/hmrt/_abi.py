@@ -77,6 +77,7 @@ PROTOTYPES = {
     "hmrt_clear_heightmap": (C.c_int, [_P]),
     "hmrt_clear_section": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "hmrt_scatter_las": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(LasTransform), C.c_int64, _P, C.c_int, C.c_int, _P]),
+    "hmrt_set_scatter_mode": (C.c_int, [_P, C.c_int]),
     "hmrt_scatter_xyz": (C.c_int, [_P, _P, C.c_int64, C.POINTER(LasTransform), _P, C.c_int, C.c_int]),
     "hmrt_build_mips": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "hmrt_resolve_colors": (C.c_int, [_P, _P, _P, C.c_int64]),

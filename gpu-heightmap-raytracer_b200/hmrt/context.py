@@ -212,6 +212,10 @@ class Context:
             C.byref(xf), first_index, self._dev(pyramid, torch.float32, "pyramid"), coarse_res, levels,
             self._dev(color_keys, torch.int64, "color_keys") if color_keys is not None else None), "hmrt_scatter_las")
 
+    def set_scatter_mode(self, mode: int):
+        """0 = auto (locality probe), 1 = direct atomics, 2 = tile-binned; results are identical."""
+        check(self.lib.hmrt_set_scatter_mode(self._h, int(mode)), "hmrt_set_scatter_mode")
+
     def scatter_xyz(self, xyz, n: int, xf: LasTransform, pyramid, coarse_res: int, levels: int):
         torch = self._torch
         self._bind_stream()

@@ -172,6 +172,12 @@ int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int rec
                      int point_format, const hmrt_las_transform* xf, int64_t first_index,
                      float* d_pyramid, int coarse_res, int levels, uint64_t* d_color_keys);
 
+/* Rasterisation strategy of hmrt_scatter_las: 0 (default) = decide per call from a locality probe of the
+ * input, 1 = one atomic max per point straight into the grid (best for survey-ordered files and small grids),
+ * 2 = bin the points by 1024 x 1024-cell tile first (best for unordered clouds on grids larger than L2).
+ * Results are bit-identical in every mode. */
+int hmrt_set_scatter_mode(hmrt_ctx* ctx, int mode);
+
 /* Same for PointdataGenerator output (PointdataGenerator/main.cpp:186-205): n float32
  * (x, y, z) triples, treated as LAS coordinates with scale 1 and offset 0. */
 int hmrt_scatter_xyz(hmrt_ctx* ctx, const float* d_xyz, int64_t n, const hmrt_las_transform* xf,
