@@ -46,3 +46,19 @@ def test_empty_heightmap_is_all_background_when_looking_up():
     cam = ol.make_camera((32.5, 10.0, 32.5), (0.0, 0.95, 0.3))
     rgb, hits = ol.cpu_trace(ol.hostsim().hostsim_trace, pyr, None, r0 >> (levels - 1), levels, 32, 24, cam, ol.make_opts(10.0))
     assert (rgb == 200).all() and not (hits["flags"] & 1).any()
+
+
+def test_arithmetic_identities_of_the_production_walk():
+    """Random-sample CPU cross-check of the FFMA.RM floor, the exact boundary FMA and the 3-operation division
+    (csrc/ray_fast.cuh).  The division is proven exhaustively on the GPU (tests/cuda/divcheck.cu, profiles/divcheck_r01.txt)."""
+    import ctypes as C
+    import subprocess
+
+    src = ol.REPO / "tests" / "hostsim" / "tricks_check.c"
+    so = ol.REPO / "tests" / "_build" / "libtricks_check.so"
+    so.parent.mkdir(parents=True, exist_ok=True)
+    subprocess.run(["gcc", "-std=c11", "-O1", "-fPIC", "-frounding-math", "-ffp-contract=off", "-shared", "-o", str(so), str(src), "-lm"], check=True)
+    lib = C.CDLL(str(so))
+    lib.tricks_check.restype = C.c_long
+    lib.tricks_check.argtypes = [C.c_uint64, C.c_long]
+    assert lib.tricks_check(12345, 20_000_000) == 0
