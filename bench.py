@@ -366,6 +366,28 @@ def run_gpu_arm(args):
         cpu = {"value": rate, "unit": "Mrays/s", "cores": n_threads, "kind": kind,
                "sample": f"8-row bands spread over the {POSES} 4K frames of the first timed pose batch, {rays} rays in {dt:.1f} s"}
 
+    # ---- the reference's own CUDA kernel, recompiled for sm_100a, on the same GPU and the same frames (reported baseline)
+    gpu_ref = None
+    ref_so = REPO / "oracle" / "_ref" / "libhmrt_ref_gpu.so"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and ref_so.exists():
+        lib = C.CDLL(str(ref_so))
+        lib.hmrt_refgpu_trace.restype = C.c_int
+        lib.hmrt_refgpu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                          C.c_int, C.POINTER(C.c_float)]
+        one = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+        total_ms, ms_f = 0.0, C.c_float()
+        cams = cams_by_step[args.warmup]
+        torch.cuda.synchronize()
+        for i in range(POSES):
+            rc = lib.hmrt_refgpu_trace(pyr.data_ptr(), None, COARSE, LEVELS, W, H, C.byref(cams, i * C.sizeof(hmrt.Camera)), 0, C.c_float(mh),
+                                       one.data_ptr(), 1, C.byref(ms_f))
+            if rc != 0:
+                raise RuntimeError(f"reference CUDA kernel failed: {rc}")
+            total_ms += ms_f.value
+        gpu_ref = {"value": POSES * W * H / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": total_ms,
+                   "what": "the reference's own cuda_rayTrace (CudaKernel.cu:195-222) recompiled for sm_100a, one launch per frame with a legal "
+                           "block shape, same B200, same pose batch (oracle/refgpu_harness.cu)"}
+
     if rank == 0:
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -375,6 +397,7 @@ def run_gpu_arm(args):
                        "parallelism": f"row tiles of 8 rows interleaved over {world} GPU(s); pyramid replicated by one NCCL broadcast",
                        "levels": LEVELS, "frame_dimension": FRAME_DIM, "pyramid_broadcast_ms": bcast_ms},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_reference_baseline": gpu_ref,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

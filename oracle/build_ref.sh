@@ -44,4 +44,15 @@ build_variant() {  # $1 = output name, $2... = extra defines
 
 build_variant libhmrt_ref -DHMRT_REF_FLOAT_MATH   # canonical: pow(float,int) in fp32 (MSVC/CUDA 8)
 build_variant libhmrt_ref_dpow                   # variant: g++/nvcc-Linux promotion to double
+
+# The reference's CUDA kernel itself, recompiled for sm_100a (baseline "reference kernel on B200").
+if command -v nvcc >/dev/null 2>&1; then
+  cp "$ref/src/CudaKernel.cu" "$tmp/CudaKernel_ref.cu"   # temp copy so that its #include "CudaKernel.cuh" finds the patched header
+  mkdir -p "$tmp/empty" && : > "$tmp/empty/math_functions.hpp"
+  sed -i '1s/^\xEF\xBB\xBF//' "$tmp/CudaKernel_ref.cu"
+  nvcc -std=c++14 -O3 -gencode arch=compute_100a,code=sm_100a -w -Xcompiler -fPIC -shared \
+       -DREF_CU="\"$tmp/CudaKernel_ref.cu\"" -I"$tmp" -I"$tmp/empty" -I"$ref/inc" -I"$here" \
+       -include climits -o "$out/libhmrt_ref_gpu.so" "$here/refgpu_harness.cu"
+  echo "built $out/libhmrt_ref_gpu.so (reference CUDA kernel for sm_100a)"
+fi
 echo "built $out/libhmrt_ref.so $out/libhmrt_ref_dpow.so"
