@@ -27,6 +27,8 @@ constexpr int kChunkW = 32, kChunkH = 4; /* a warp's unit of work: four 8 x 4 pi
 constexpr int kStageRow = kChunkW * 3;   /* 96 bytes of RGB8 per chunk row */
 static_assert(HMRT_ROW_TILE == 2 * kChunkH, "a row tile is two chunk rows");
 
+constexpr uint32_t kInKernelTopMax = 1024; /* top levels up to this many cells are reduced inside the trace kernel */
+
 /* device-side scratch refreshed by the launcher (16 bytes) */
 struct TraceScratch {
   uint32_t hmax_key;             /* order-preserving key of max(top level), see top_level_max_kernel */
@@ -45,7 +47,7 @@ struct TraceParams {
   int rows_local;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
-  const uint32_t* hmax_key;          /* &scratch[0].hmax_key */
+  const uint32_t* hmax_key;          /* &scratch[0].hmax_key, or nullptr: every CTA reduces the (small) top level itself */
   unsigned long long* next_chunk;    /* this launch's work counter */
   uint32_t chunks_x;               /* ceil(W / 32) */
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
@@ -92,9 +94,20 @@ __global__ void __launch_bounds__(kThreads) trace_persistent_kernel(const __grid
   uint32_t tab = 0; /* shared-window address of the level table, pinned in a register */
   float hmax = 0.0f;
   if (WALK != kWalkReference) {
-    hmax = key_to_float(__ldg(p.hmax_key));
+    __shared__ uint32_t hmax_s;
+    if (threadIdx.x == 0) hmax_s = 0;
     fill_level_table(level_tab, p.grid);
     __syncthreads();
+    if (p.hmax_key) {
+      hmax = key_to_float(__ldg(p.hmax_key));
+    } else { /* top level of at most 1024 cells: cheaper than a separate launch per call */
+      uint32_t k = 0;
+      for (uint32_t i = threadIdx.x; i < p.grid.coarse_sq; i += kThreads) k = max(k, float_to_key(__ldg(p.grid.pyramid + i)));
+      k = __reduce_max_sync(0xffffffffu, k);
+      if ((threadIdx.x & 31) == 0 && k) atomicMax(&hmax_s, k);
+      __syncthreads();
+      hmax = key_to_float(hmax_s);
+    }
     tab = (uint32_t)__cvta_generic_to_shared(level_tab);
     asm volatile("" : "+r"(tab));
   }
@@ -202,9 +215,9 @@ static int prepare_trace(hmrt_ctx* ctx, int slots) {
   if (rc) return rc;
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
   HMRT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(TraceScratch) * (size_t)slots, ctx->stream));
-  if (ctx->trace_variant == 0) {
+  if (ctx->trace_variant == 0 && ctx->grid.coarse_sq > kInKernelTopMax) {
     const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
-    const unsigned blocks = (unsigned)((n_top + 4095u) / 4096u);
+    const unsigned blocks = (unsigned)((n_top + 1023u) / 1024u); /* 4 values per thread: short dependent chains */
     top_level_max_kernel<<<blocks > 1184u ? 1184u : blocks, 256, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, &scratch->hmax_key);
     HMRT_LAUNCHED(ctx);
   }
@@ -263,7 +276,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   p.chunks_per_frame = (uint32_t)local_tiles * 2u * p.chunks_x;
   p.total_chunks = (unsigned long long)p.chunks_per_frame * (unsigned long long)n_frames;
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
-  p.hmax_key = &scratch[0].hmax_key;
+  p.hmax_key = ctx->grid.coarse_sq > kInKernelTopMax ? &scratch[0].hmax_key : nullptr;
   p.next_chunk = &scratch[slot].next_chunk;
 
   if (n_frames == 1) {

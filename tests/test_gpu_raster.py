@@ -211,3 +211,39 @@ def test_binned_scatter_equals_direct(cuda_ctx, skew):
     cuda_ctx.scatter_las(rec[:200_000], 200_000, 20, 0, xf, pyr, coarse, levels)
     torch.cuda.synchronize()
     assert torch.equal(pyr[idx[0]:].cpu().view(torch.int32), torch.from_numpy(want[idx[0]:]).view(torch.int32))
+
+
+def test_baseline_config_1_end_to_end(cuda_ctx):
+    """BASELINE configs[0] exactly: seeded PointdataGenerator terrain -> 1024^2 heightmap (8 levels) -> one 640x480
+    primary-ray frame, camera at the grid centre at 1.5 x max height looking along normalize(0, -0.9, 1) (main.cpp:56).
+    GPU pipeline (scatter_xyz + build_mips + trace) against the same pipeline on the CPU oracle, and -- when the
+    reference's own code is available -- against oracle/_ref."""
+    import gpulib
+    from hmrt import LasTransform
+
+    n, W, H = 1024, 640, 480
+    xyz = np.zeros(((n + 1) ** 2, 3), np.float32)
+    assert ol.oracle().hmrt_oracle_pdg_generate(n, 1, xyz.ctypes.data) == 0
+    xf = LasTransform()
+    xf.scale[:] = (1.0, 1.0, 1.0)
+    xf.cell_size[:] = (1.0, 1.0, 1.0)
+    res, idx, total = ol.pyramid_layout(8, 8)
+    want_pyr = np.zeros(total, np.float32)
+    assert ol.oracle().hmrt_oracle_rasterise_xyz(xyz.ctypes.data, len(xyz), C.byref(xf), want_pyr.ctypes.data, 8, 8) == 0
+    pyr = torch.empty(total, dtype=torch.float32, device="cuda")
+    cuda_ctx.clear_section(pyr, 8, 8)
+    cuda_ctx.scatter_xyz(torch.from_numpy(xyz).cuda(), len(xyz), xf, pyr, 8, 8)
+    cuda_ctx.build_mips(pyr, 8, 8)
+    torch.cuda.synchronize()
+    assert (pyr.cpu().numpy().view(np.uint32) == want_pyr.view(np.uint32)).all()
+    mh = float(want_pyr[:64].max())
+    cuda_ctx.set_heightmap(pyr, None, 8, 8, mh)
+    cam = ol.make_camera((512.0, 1.5 * mh, 512.0), (0.0, -0.9, 1.0))
+    opts = ol.make_opts(mh)
+    got = gpulib.gpu_trace(cuda_ctx, W, H, [cam], opts)
+    want = ol.cpu_trace(ol.oracle().hmrt_oracle_trace, want_pyr, None, 8, 8, W, H, cam, opts)
+    ol.assert_same_trace((got[0][0], got[1][0]), want, "config 1 vs oracle")
+    if ol.ref() is not None:
+        ref = ol.cpu_trace(ol.ref().hmrt_ref_trace, want_pyr, None, 8, 8, W, H, cam, opts)
+        ol.assert_same_trace((got[0][0], got[1][0]), ref, "config 1 vs the reference's own code")
+    assert (got[1][0]["flags"] & 1).mean() > 0.9
