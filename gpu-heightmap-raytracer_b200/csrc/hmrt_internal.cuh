@@ -36,7 +36,7 @@ struct hmrt_ctx {
   float init_max_height;
   void* d_scratch;    /* TraceScratch[scratch_cap]: max(top level) key + one work counter per launch of a call */
   int scratch_cap;
-  int ctas_per_sm[6]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
+  int ctas_per_sm[12]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;
   int frames_cap;

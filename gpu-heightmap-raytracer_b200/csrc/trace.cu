@@ -32,7 +32,7 @@ constexpr uint32_t kInKernelTopMax = 1024; /* top levels up to this many cells a
 /* device-side scratch refreshed by the launcher (16 bytes) */
 struct TraceScratch {
   uint32_t hmax_key;             /* order-preserving key of max(top level), see top_level_max_kernel */
-  uint32_t pad;
+  uint32_t next_tail;            /* work counter of the tile-granular tail */
   unsigned long long next_chunk; /* work counter of the persistent kernel */
 };
 
@@ -48,7 +48,10 @@ struct TraceParams {
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
   const uint32_t* hmax_key;          /* &scratch[0].hmax_key, or nullptr: every CTA reduces the (small) top level itself */
-  unsigned long long* next_chunk;    /* this launch's work counter */
+  unsigned long long* next_chunk;    /* this launch's work counter (whole chunks) */
+  uint32_t* next_tail;               /* ... and the counter of the tile-granular tail */
+  unsigned long long bulk_chunks;    /* chunks [0, bulk_chunks) are claimed whole, the rest tile by tile */
+  uint32_t tail_tiles;               /* 4 * (total_chunks - bulk_chunks) */
   uint32_t chunks_x;               /* ceil(W / 32) */
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
   unsigned long long total_chunks; /* frames * chunks_per_frame */
@@ -80,17 +83,100 @@ __global__ void __launch_bounds__(256) top_level_max_kernel(const float* __restr
  * (ray_core.cuh), kept as the in-library parity reference (hmrt_set_trace_variant). */
 enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2 };
 
+/* One unit of work of a warp: the tiles [k_first, k_last) of chunk `chunk` (all four in the bulk phase -> 128-bit
+ * stores; a single one in the tail phase -> 8-byte stores). */
+template <bool HITS, int WALK, bool TAIL>
+__device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, float hmax, FrameConsts* frame_slot,
+                                           uint8_t (*stage)[kStageRow], unsigned long long chunk, int k_first, int k_last) {
+  const int lane = threadIdx.x & 31;
+  const int lx = lane & 7, ly = lane >> 3; /* 8 x 4 lanes */
+  /* chunk -> (frame, local row tile j, 4-row half, 32-pixel column group); consecutive chunks are
+   * neighbours along x, so concurrently running warps cover a compact band of the frame */
+  const uint32_t frame = (uint32_t)(chunk / p.chunks_per_frame);
+  const uint32_t in_frame = (uint32_t)(chunk - (unsigned long long)frame * p.chunks_per_frame);
+  const uint32_t strip = in_frame / p.chunks_x, cx = in_frame - strip * p.chunks_x;
+  const int j = (int)(strip >> 1), half = (int)(strip & 1u);
+  const int tile = p.tile_first + j * p.tile_stride;         /* 8-row tile in the frame */
+  const int row0 = tile * HMRT_ROW_TILE + half * kChunkH;    /* first row of the chunk in the frame */
+  const int row0_local = j * HMRT_ROW_TILE + half * kChunkH; /* ... in this call's output */
+  const int py = row0 + ly;
+  const int x0 = (int)cx * kChunkW;
+  const size_t frame_base = (size_t)frame * ((size_t)p.rows_local * (size_t)p.W);
+
+  /* frame constants -> the warp's shared slot (read back at the start of every ray; keeping the 16
+   * floats in registers across the walk costs a whole CTA of occupancy) */
+  if (lane < 4) {
+    const float4* src = p.frames ? reinterpret_cast<const float4*>(p.frames + frame) : reinterpret_cast<const float4*>(&p.frame0);
+    reinterpret_cast<float4*>(frame_slot)[lane] = src[lane];
+  }
+  __syncwarp();
+  const FrameConsts& f = *frame_slot;
+
+#pragma unroll 1
+  for (int k = k_first; k < k_last; ++k) { /* the 8 x 4 tiles of the unit */
+    const int tx = k * 8 + lx;
+    const int px = x0 + tx;
+    if (px < p.W && py < p.H) {
+      RayResult r;
+      if (WALK == kWalkFastPow2)
+        r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+      else if (WALK == kWalkFast)
+        r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+      else
+        r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
+      stage[ly][tx * 3 + 0] = r.r;
+      stage[ly][tx * 3 + 1] = r.g;
+      stage[ly][tx * 3 + 2] = r.b;
+      if (HITS)
+        reinterpret_cast<float4*>(p.hits)[frame_base + (size_t)(row0_local + ly) * p.W + px] =
+            make_float4(r.pos.x, r.pos.y, r.pos.z, __uint_as_float(r.flags));
+    }
+  }
+  __syncwarp();
+
+  uint8_t* out = p.rgb + frame_base * 3;
+  const int xa = x0 + k_first * 8, xb = min(x0 + k_last * 8, p.W); /* pixel columns produced by this unit */
+  const bool full = (x0 + k_last * 8 <= p.W) && (row0 + kChunkH <= p.H);
+  if (!TAIL && p.vec_store && full) {
+    /* 4 rows x 6 pieces of 16 B; (x0 * 3) % 16 == 0 because x0 is a multiple of 32 */
+    if (lane < kChunkH * 6) {
+      const int r = lane / 6, c = lane % 6;
+      const uint4 v = *reinterpret_cast<const uint4*>(&stage[r][c * 16]);
+      *reinterpret_cast<uint4*>(out + ((size_t)(row0_local + r) * p.W + x0) * 3 + c * 16) = v;
+    }
+  } else if (TAIL && p.vec_store && full) {
+    /* one 8 x 4 tile: 4 rows x 3 pieces of 8 B (24-byte rows are 8-byte aligned when W % 16 == 0) */
+    if (lane < kChunkH * 3) {
+      const int r = lane / 3, c = lane % 3;
+      const uint2 v = *reinterpret_cast<const uint2*>(&stage[r][k_first * 24 + c * 8]);
+      *reinterpret_cast<uint2*>(out + ((size_t)(row0_local + r) * p.W + xa) * 3 + c * 8) = v;
+    }
+  } else {
+    const int valid_h = min(kChunkH, p.H - row0);
+    const int b0 = (xa - x0) * 3, b1 = (xb - x0) * 3;
+    for (int i = lane; i < kChunkH * kStageRow; i += 32) {
+      const int r = i / kStageRow, b = i % kStageRow;
+      if (r < valid_h && b >= b0 && b < b1) out[((size_t)(row0_local + r) * p.W + x0) * 3 + b] = stage[r][b];
+    }
+  }
+  __syncwarp(); /* the stage slice is reused by the next unit */
+}
+
 /*
  * Persistent traversal kernel (see the file header).  There is no CTA-wide barrier after the
  * prologue: a warp that finishes a cheap (sky) chunk immediately claims the next one instead of
  * idling at a tile barrier (ncu r01: 17 % of the resident warps were parked at the barrier of the
- * former one-tile-per-CTA kernel).
+ * former one-tile-per-CTA kernel).  Bulk phase: whole 32 x 4 chunks.  Tail phase: the last
+ * "one chunk per resident warp" is handed out tile by tile (8 x 4), so all warps finish within one
+ * tile's time of each other -- that matters for single-frame launches (interactive use, the per-frame
+ * launches of hmrt_trace_host, 1/8 frames on 8 GPUs).  TAILED = false compiles the tail out: for launches
+ * with hundreds of chunks per warp the tail is irrelevant and the leaner code is ~1.5 % faster (measured).
  */
-template <bool HITS, int WALK>
+template <bool HITS, int WALK, bool TAILED>
 __global__ void __launch_bounds__(kThreads) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kWarps][kChunkH][kStageRow];
   __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
-  __shared__ __align__(16) FrameConsts frame_s[kWarps]; /* the frame constants of each warp's current chunk */
+  __shared__ __align__(16) FrameConsts frame_s[kWarps]; /* the frame constants of each warp's current unit */
   uint32_t tab = 0; /* shared-window address of the level table, pinned in a register */
   float hmax = 0.0f;
   if (WALK != kWalkReference) {
@@ -111,82 +197,31 @@ __global__ void __launch_bounds__(kThreads) trace_persistent_kernel(const __grid
     tab = (uint32_t)__cvta_generic_to_shared(level_tab);
     asm volatile("" : "+r"(tab));
   }
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lx = lane & 7, ly = lane >> 3; /* 8 x 4 lanes */
-  const size_t frame_px = (size_t)p.rows_local * (size_t)p.W;
 
-  for (;;) {
-    unsigned long long chunk = 0;
-    if (lane == 0) chunk = atomicAdd(p.next_chunk, 1ull);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (chunk >= p.total_chunks) break;
-    /* chunk -> (frame, local row tile j, 4-row half, 32-pixel column group); consecutive chunks are
-     * neighbours along x, so concurrently running warps cover a compact band of the frame */
-    const uint32_t frame = (uint32_t)(chunk / p.chunks_per_frame);
-    const uint32_t in_frame = (uint32_t)(chunk - (unsigned long long)frame * p.chunks_per_frame);
-    const uint32_t strip = in_frame / p.chunks_x, cx = in_frame - strip * p.chunks_x;
-    const int j = (int)(strip >> 1), half = (int)(strip & 1u);
-    const int tile = p.tile_first + j * p.tile_stride;         /* 8-row tile in the frame */
-    const int row0 = tile * HMRT_ROW_TILE + half * kChunkH;    /* first row of the chunk in the frame */
-    const int row0_local = j * HMRT_ROW_TILE + half * kChunkH; /* ... in this call's output */
-    const int py = row0 + ly;
-    const int x0 = (int)cx * kChunkW;
-    const size_t frame_base = (size_t)frame * frame_px;
-
-    /* frame constants -> the warp's shared slot (read back at the start of every ray; keeping the 16
-     * floats in registers across the walk costs a whole CTA of occupancy) */
-    if (lane < 4) {
-      const float4* src = p.frames ? reinterpret_cast<const float4*>(p.frames + frame) : reinterpret_cast<const float4*>(&p.frame0);
-      reinterpret_cast<float4*>(&frame_s[warp])[lane] = src[lane];
+  for (;;) { /* bulk */
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(p.next_chunk, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= p.bulk_chunks) break;
+    trace_unit<HITS, WALK, false>(p, tab, hmax, &frame_s[warp], stage[warp], c, 0, 4);
+  }
+  if (TAILED) {
+    for (;;) { /* tail */
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(p.next_tail, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= p.tail_tiles) break;
+      const int k = (int)(t & 3u);
+      trace_unit<HITS, WALK, true>(p, tab, hmax, &frame_s[warp], stage[warp], p.bulk_chunks + (t >> 2), k, k + 1);
     }
-    __syncwarp();
-    const FrameConsts& f = frame_s[warp];
-
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) { /* the four 8 x 4 tiles of the chunk */
-      const int tx = k * 8 + lx;
-      const int px = x0 + tx;
-      if (px < p.W && py < p.H) {
-        RayResult r;
-        if (WALK == kWalkFastPow2)
-          r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
-        else if (WALK == kWalkFast)
-          r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
-        else
-          r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
-        stage[warp][ly][tx * 3 + 0] = r.r;
-        stage[warp][ly][tx * 3 + 1] = r.g;
-        stage[warp][ly][tx * 3 + 2] = r.b;
-        if (HITS)
-          reinterpret_cast<float4*>(p.hits)[frame_base + (size_t)(row0_local + ly) * p.W + px] =
-              make_float4(r.pos.x, r.pos.y, r.pos.z, __uint_as_float(r.flags));
-      }
-    }
-    __syncwarp();
-
-    uint8_t* out = p.rgb + frame_base * 3;
-    const bool full = (x0 + kChunkW <= p.W) && (row0 + kChunkH <= p.H);
-    if (p.vec_store && full) {
-      /* 4 rows x 6 pieces of 16 B; (x0 * 3) % 16 == 0 because x0 is a multiple of 32 */
-      if (lane < kChunkH * 6) {
-        const int r = lane / 6, c = lane % 6;
-        const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][r][c * 16]);
-        *reinterpret_cast<uint4*>(out + ((size_t)(row0_local + r) * p.W + x0) * 3 + c * 16) = v;
-      }
-    } else {
-      const int valid_w = min(kChunkW, p.W - x0), valid_h = min(kChunkH, p.H - row0);
-      for (int i = lane; i < kChunkH * kStageRow; i += 32) {
-        const int r = i / kStageRow, b = i % kStageRow;
-        if (r < valid_h && b < valid_w * 3) out[((size_t)(row0_local + r) * p.W + x0) * 3 + b] = stage[warp][r][b];
-      }
-    }
-    __syncwarp(); /* the stage slice is reused by the next chunk */
   }
 }
 
-static const void* pick_kernel(bool hits, int walk) {
-#define HMRT_PICK(HITS_, WALK_) return reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_>)
+static const void* pick_kernel(bool hits, int walk, bool tailed) {
+#define HMRT_PICK(HITS_, WALK_)                                                                         \
+  return tailed ? reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, true>)           \
+                : reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, false>)
   if (hits) {
     if (walk == kWalkFastPow2) HMRT_PICK(true, kWalkFastPow2);
     if (walk == kWalkFast) HMRT_PICK(true, kWalkFast);
@@ -278,6 +313,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
   p.hmax_key = ctx->grid.coarse_sq > kInKernelTopMax ? &scratch[0].hmax_key : nullptr;
   p.next_chunk = &scratch[slot].next_chunk;
+  p.next_tail = &scratch[slot].next_tail;
 
   if (n_frames == 1) {
     make_frame_consts(cams[0], p.frame0);
@@ -299,8 +335,10 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   const bool pow2 = (ctx->grid.coarse_res & (ctx->grid.coarse_res - 1)) == 0;
   const int walk = ctx->trace_variant != 0 ? kWalkReference : (pow2 ? kWalkFastPow2 : kWalkFast);
   /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
-  const void* fn = pick_kernel(d_hits != nullptr, walk);
-  const int kslot = (d_hits ? 3 : 0) + walk;
+  /* tile-granular tail only where it pays: fewer than 64 chunks per resident warp (see the kernel comment) */
+  const bool tailed = p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
+  const void* fn = pick_kernel(d_hits != nullptr, walk, tailed);
+  const int kslot = (tailed ? 6 : 0) + (d_hits ? 3 : 0) + walk;
   if (ctx->ctas_per_sm[kslot] == 0) {
     int per_sm = 0;
     HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
@@ -309,6 +347,11 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   const unsigned long long want = (p.total_chunks + kWarps - 1) / kWarps;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
+  /* the last "one chunk per resident warp" is distributed tile by tile */
+  unsigned long long tail_chunks = p.total_chunks < (unsigned long long)grid * kWarps ? p.total_chunks : (unsigned long long)grid * kWarps;
+  if (!tailed) tail_chunks = 0;
+  p.bulk_chunks = p.total_chunks - tail_chunks;
+  p.tail_tiles = (uint32_t)(tail_chunks * 4ull);
   void* args[] = {&p};
   HMRT_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
   HMRT_LAUNCHED(ctx);

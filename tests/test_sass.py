@@ -44,7 +44,7 @@ def test_every_kernel_is_present(sass):
 
 def test_packed_walk_is_not_contracted(sass):
     prod = {n: ins for n, ins in sass.items() if "trace_persistent_kernel" in n and ("ELi1E" in n or "ELi2E" in n)}
-    assert len(prod) == 4  # {hits, no hits} x {pow2, generic}
+    assert len(prod) == 8  # {hits, no hits} x {pow2, generic} x {tile-granular tail, none}
     for name, ins in prod.items():
         floor_rm = sum(i.startswith("FFMA2.RM") for i in ins)
         ffma2 = sum(i.startswith("FFMA2 ") for i in ins)
