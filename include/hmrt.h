@@ -167,7 +167,9 @@ int hmrt_clear_section(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int leve
  *   first_index  global index of record 0 (file order), used for the colour keys
  *   d_color_keys  optional, res0^2 uint64: keeps (index+1)<<24 | rgb of the LAST point in file
  *                 order per cell (the reference's last-writer-wins, main.cpp:223-224)
- * Points outside [0,res0)^2 or with classification 7 are skipped (main.cpp:209). */
+ * Points outside [0,res0)^2 or with classification 7 are skipped (main.cpp:209).
+ * Asynchronous on the context's stream, except that in scatter mode 0 a call with >= 4 M points on a grid of
+ * >= 64 tiles first reads back a 4 KB locality probe (one stream synchronisation) to choose its path. */
 int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len,
                      int point_format, const hmrt_las_transform* xf, int64_t first_index,
                      float* d_pyramid, int coarse_res, int levels, uint64_t* d_color_keys);
