@@ -235,6 +235,23 @@ def run_reference_arm(args):
 # GPU arm
 
 def run_gpu_arm(args):
+    # Libraries (NCCL's version banner, for one) write to stdout; the contract is ONE JSON line there.
+    # Everything until the final print goes to stderr instead.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_gpu_arm(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
@@ -399,11 +416,12 @@ def run_gpu_arm(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_reference_baseline": gpu_ref,
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return line
 
 
 def main():

@@ -14,6 +14,8 @@
  * coalesced 128-bit stores (byte stores when W % 16 != 0 or on ragged edges).  Many frames
  * (a fly-through, a batch of camera poses) run in ONE launch.
  */
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hmrt_internal.cuh"
@@ -27,7 +29,8 @@ constexpr int kChunkW = 32, kChunkH = 4; /* a warp's unit of work: four 8 x 4 pi
 constexpr int kStageRow = kChunkW * 3;   /* 96 bytes of RGB8 per chunk row */
 static_assert(HMRT_ROW_TILE == 2 * kChunkH, "a row tile is two chunk rows");
 
-constexpr uint32_t kInKernelTopMax = 1024; /* top levels up to this many cells are reduced inside the trace kernel */
+constexpr int kInlineFrames = 48;        /* frames whose constants fit in the kernel parameters */
+constexpr uint32_t kPrepTopMax = 65536;  /* top levels up to this many cells are reduced by the one-CTA prep kernel */
 
 /* device-side scratch refreshed by the launcher (16 bytes) */
 struct TraceScratch {
@@ -39,15 +42,14 @@ struct TraceScratch {
 struct TraceParams {
   Grid grid;
   Shading shading;
-  alignas(16) FrameConsts frame0; /* used when frames == nullptr (single-frame launch); read as 4 x float4 */
-  const FrameConsts* frames; /* device array, one per frame */
+  const FrameConsts* frames; /* device array, one per frame; nullptr: the frames travel in frame_inline */
   uint8_t* rgb;
   hmrt_hit* hits;
   int W, H;
   int rows_local;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
-  const uint32_t* hmax_key;          /* &scratch[0].hmax_key, or nullptr: every CTA reduces the (small) top level itself */
+  const uint32_t* hmax_key;          /* &scratch[0].hmax_key */
   unsigned long long* next_chunk;    /* this launch's work counter (whole chunks) */
   uint32_t* next_tail;               /* ... and the counter of the tile-granular tail */
   unsigned long long bulk_chunks;    /* chunks [0, bulk_chunks) are claimed whole, the rest tile by tile */
@@ -55,7 +57,11 @@ struct TraceParams {
   uint32_t chunks_x;               /* ceil(W / 32) */
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
   unsigned long long total_chunks; /* frames * chunks_per_frame */
+  /* up to kInlineFrames per-frame constants ride in the kernel parameters: no host->device copy in front
+   * of the launch (a 16-frame call spent ~27 us of device timeline on that copy) */
+  alignas(16) FrameConsts frame_inline[kInlineFrames];
 };
+static_assert(sizeof(TraceParams) <= 4096, "kernel parameter space");
 
 /* float <-> unsigned key with the same ordering (so an unsigned atomicMax is a float max) */
 __device__ __forceinline__ uint32_t float_to_key(float f) {
@@ -77,6 +83,40 @@ __global__ void __launch_bounds__(256) top_level_max_kernel(const float* __restr
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) k = max(k, float_to_key(__ldg(top + i)));
   k = __reduce_max_sync(0xffffffffu, k);
   if ((threadIdx.x & 31) == 0 && k) atomicMax(out, k);
+}
+
+/*
+ * One-CTA preparation kernel in front of every trace call: zeroes the work counters of the call's launches and,
+ * for top levels of up to kPrepTopMax cells (256^2: every BASELINE configuration), reduces the top-level maximum
+ * itself -- one small launch instead of a memset, a reduction launch and (for multi-frame calls) a parameter copy.
+ */
+__global__ void __launch_bounds__(1024) trace_prep_kernel(const float* __restrict__ top, uint32_t n_top, TraceScratch* scratch, int slots,
+                                                          int reduce_here) {
+  __shared__ uint32_t warp_max[32];
+  for (int s = threadIdx.x; s < slots; s += blockDim.x) {
+    scratch[s].next_chunk = 0ull;
+    scratch[s].next_tail = 0u;
+    if (s > 0 || !reduce_here) scratch[s].hmax_key = 0u; /* slot 0: written below, or by top_level_max_kernel */
+  }
+  if (!reduce_here) return;
+  uint32_t k = 0;
+  if ((reinterpret_cast<uintptr_t>(top) & 15) == 0) { /* 16-byte loads: 4 per thread for a 128^2 top level */
+    const uint32_t n4 = n_top >> 2;
+    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(top) + i);
+      k = max(max(k, float_to_key(v.x)), max(float_to_key(v.y), max(float_to_key(v.z), float_to_key(v.w))));
+    }
+    for (uint32_t i = (n4 << 2) + threadIdx.x; i < n_top; i += blockDim.x) k = max(k, float_to_key(__ldg(top + i)));
+  } else {
+    for (uint32_t i = threadIdx.x; i < n_top; i += blockDim.x) k = max(k, float_to_key(__ldg(top + i)));
+  }
+  k = __reduce_max_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    k = __reduce_max_sync(0xffffffffu, warp_max[threadIdx.x]);
+    if (threadIdx.x == 0) scratch[0].hmax_key = k;
+  }
 }
 
 /* WALK: kWalkFast* = production walk (ray_fast.cuh); kWalkReference = operation-by-operation walk
@@ -106,7 +146,7 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
   /* frame constants -> the warp's shared slot (read back at the start of every ray; keeping the 16
    * floats in registers across the walk costs a whole CTA of occupancy) */
   if (lane < 4) {
-    const float4* src = p.frames ? reinterpret_cast<const float4*>(p.frames + frame) : reinterpret_cast<const float4*>(&p.frame0);
+    const float4* src = reinterpret_cast<const float4*>(p.frames ? p.frames + frame : &p.frame_inline[frame]);
     reinterpret_cast<float4*>(frame_slot)[lane] = src[lane];
   }
   __syncwarp();
@@ -173,27 +213,16 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
  * with hundreds of chunks per warp the tail is irrelevant and the leaner code is ~1.5 % faster (measured).
  */
 template <bool HITS, int WALK, bool TAILED>
-__global__ void __launch_bounds__(kThreads) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(kThreads, TAILED ? 5 : 0) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kWarps][kChunkH][kStageRow];
   __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
   __shared__ __align__(16) FrameConsts frame_s[kWarps]; /* the frame constants of each warp's current unit */
   uint32_t tab = 0; /* shared-window address of the level table, pinned in a register */
   float hmax = 0.0f;
   if (WALK != kWalkReference) {
-    __shared__ uint32_t hmax_s;
-    if (threadIdx.x == 0) hmax_s = 0;
+    hmax = key_to_float(__ldg(p.hmax_key));
     fill_level_table(level_tab, p.grid);
     __syncthreads();
-    if (p.hmax_key) {
-      hmax = key_to_float(__ldg(p.hmax_key));
-    } else { /* top level of at most 1024 cells: cheaper than a separate launch per call */
-      uint32_t k = 0;
-      for (uint32_t i = threadIdx.x; i < p.grid.coarse_sq; i += kThreads) k = max(k, float_to_key(__ldg(p.grid.pyramid + i)));
-      k = __reduce_max_sync(0xffffffffu, k);
-      if ((threadIdx.x & 31) == 0 && k) atomicMax(&hmax_s, k);
-      __syncthreads();
-      hmax = key_to_float(hmax_s);
-    }
     tab = (uint32_t)__cvta_generic_to_shared(level_tab);
     asm volatile("" : "+r"(tab));
   }
@@ -249,10 +278,13 @@ static int prepare_trace(hmrt_ctx* ctx, int slots) {
   int rc = ensure_scratch(ctx, slots);
   if (rc) return rc;
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
-  HMRT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(TraceScratch) * (size_t)slots, ctx->stream));
-  if (ctx->trace_variant == 0 && ctx->grid.coarse_sq > kInKernelTopMax) {
-    const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
-    const unsigned blocks = (unsigned)((n_top + 1023u) / 1024u); /* 4 values per thread: short dependent chains */
+  const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
+  const bool need_hmax = ctx->trace_variant == 0;
+  const int reduce_here = need_hmax && n_top <= kPrepTopMax;
+  trace_prep_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, scratch, slots, reduce_here);
+  HMRT_LAUNCHED(ctx);
+  if (need_hmax && !reduce_here) { /* huge top level (e.g. a single-level "flat DDA" map): multi-CTA reduction */
+    const unsigned blocks = (unsigned)((n_top + 1023u) / 1024u);
     top_level_max_kernel<<<blocks > 1184u ? 1184u : blocks, 256, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, &scratch->hmax_key);
     HMRT_LAUNCHED(ctx);
   }
@@ -311,12 +343,12 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   p.chunks_per_frame = (uint32_t)local_tiles * 2u * p.chunks_x;
   p.total_chunks = (unsigned long long)p.chunks_per_frame * (unsigned long long)n_frames;
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
-  p.hmax_key = ctx->grid.coarse_sq > kInKernelTopMax ? &scratch[0].hmax_key : nullptr;
+  p.hmax_key = &scratch[0].hmax_key;
   p.next_chunk = &scratch[slot].next_chunk;
   p.next_tail = &scratch[slot].next_tail;
 
-  if (n_frames == 1) {
-    make_frame_consts(cams[0], p.frame0);
+  if (n_frames <= kInlineFrames) {
+    for (int i = 0; i < n_frames; ++i) make_frame_consts(cams[i], p.frame_inline[i]);
     p.frames = nullptr;
   } else {
     int rc = ensure_frames(ctx, frames_at + n_frames);
@@ -343,6 +375,12 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
     int per_sm = 0;
     HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     ctx->ctas_per_sm[kslot] = per_sm < 1 ? 1 : per_sm;
+    if (getenv("HMRT_DEBUG")) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, fn);
+      fprintf(stderr, "hmrt: trace kernel slot %d: %d regs, %zu B static smem, %zu B local -> %d CTAs/SM\n", kslot, fa.numRegs, fa.sharedSizeBytes,
+              fa.localSizeBytes, per_sm);
+    }
   }
   const unsigned long long want = (p.total_chunks + kWarps - 1) / kWarps;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
