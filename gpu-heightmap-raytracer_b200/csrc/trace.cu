@@ -445,7 +445,9 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
   /* frames per launch: enough rays (>= ~4 M) to amortise launch + tail, e.g. 1 whole 4K frame on one
    * GPU, 4 frames when a rank only owns 1/8 of every frame */
   const size_t rays_per_frame = frame_bytes / 3;
-  int group = (int)((4000000 + rays_per_frame - 1) / rays_per_frame);
+  size_t group_rays = 4000000;
+  if (const char* e = getenv("HMRT_HOST_GROUP_RAYS")) group_rays = (size_t)atoll(e); /* tuning knob */
+  int group = (int)((group_rays + rays_per_frame - 1) / rays_per_frame);
   if (group < 1) group = 1;
   if (group > n_frames) group = n_frames;
   const int n_launches = (n_frames + group - 1) / group;
