@@ -36,7 +36,8 @@ constexpr uint32_t kPrepTopMax = 65536;  /* top levels up to this many cells are
 struct TraceScratch {
   uint32_t hmax_key;             /* order-preserving key of max(top level), see top_level_max_kernel */
   uint32_t next_tail;            /* work counter of the tile-granular tail */
-  unsigned long long next_chunk; /* work counter of the persistent kernel */
+  uint32_t next_chunk;           /* work counter of the persistent kernel (whole chunks) */
+  uint32_t pad;
 };
 
 struct TraceParams {
@@ -50,13 +51,13 @@ struct TraceParams {
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
   const uint32_t* hmax_key;          /* &scratch[0].hmax_key */
-  unsigned long long* next_chunk;    /* this launch's work counter (whole chunks) */
+  uint32_t* next_chunk;              /* this launch's work counter (whole chunks) */
   uint32_t* next_tail;               /* ... and the counter of the tile-granular tail */
-  unsigned long long bulk_chunks;    /* chunks [0, bulk_chunks) are claimed whole, the rest tile by tile */
+  uint32_t bulk_chunks;              /* chunks [0, bulk_chunks) are claimed whole, the rest tile by tile */
   uint32_t tail_tiles;               /* 4 * (total_chunks - bulk_chunks) */
   uint32_t chunks_x;               /* ceil(W / 32) */
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
-  unsigned long long total_chunks; /* frames * chunks_per_frame */
+  uint32_t total_chunks;           /* frames * chunks_per_frame (< 2^31: larger calls are split by the launcher) */
   /* up to kInlineFrames per-frame constants ride in the kernel parameters: no host->device copy in front
    * of the launch (a 16-frame call spent ~27 us of device timeline on that copy) */
   alignas(16) FrameConsts frame_inline[kInlineFrames];
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(1024) trace_prep_kernel(const float* __restric
                                                           int reduce_here) {
   __shared__ uint32_t warp_max[32];
   for (int s = threadIdx.x; s < slots; s += blockDim.x) {
-    scratch[s].next_chunk = 0ull;
+    scratch[s].next_chunk = 0u;
     scratch[s].next_tail = 0u;
     if (s > 0 || !reduce_here) scratch[s].hmax_key = 0u; /* slot 0: written below, or by top_level_max_kernel */
   }
@@ -127,14 +128,18 @@ enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2 };
  * stores; a single one in the tail phase -> 8-byte stores). */
 template <bool HITS, int WALK, bool TAIL>
 __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, float hmax, FrameConsts* frame_slot,
-                                           uint8_t (*stage)[kStageRow], unsigned long long chunk, int k_first, int k_last) {
+                                           uint8_t (*stage)[kStageRow], uint32_t chunk, int k_first, int k_last) {
   const int lane = threadIdx.x & 31;
   const int lx = lane & 7, ly = lane >> 3; /* 8 x 4 lanes */
   /* chunk -> (frame, local row tile j, 4-row half, 32-pixel column group); consecutive chunks are
    * neighbours along x, so concurrently running warps cover a compact band of the frame */
-  const uint32_t frame = (uint32_t)(chunk / p.chunks_per_frame);
-  const uint32_t in_frame = (uint32_t)(chunk - (unsigned long long)frame * p.chunks_per_frame);
-  const uint32_t strip = in_frame / p.chunks_x, cx = in_frame - strip * p.chunks_x;
+  const uint32_t frame = chunk / p.chunks_per_frame;
+  const uint32_t in_frame = chunk - frame * p.chunks_per_frame;
+  /* rows are visited from the top of the frame down: the far / near-horizon rows hold the longest walks, so they
+   * are claimed first and the launch drains on the short, uniform walks of the bottom rows (longest-processing-
+   * time-first; measured: the drain of a 1/8-frame-share launch cost ~5 % with bottom-up order) */
+  const uint32_t strip_up = in_frame / p.chunks_x, cx = in_frame - strip_up * p.chunks_x;
+  const uint32_t strip = p.chunks_per_frame / p.chunks_x - 1u - strip_up;
   const int j = (int)(strip >> 1), half = (int)(strip & 1u);
   const int tile = p.tile_first + j * p.tile_stride;         /* 8-row tile in the frame */
   const int row0 = tile * HMRT_ROW_TILE + half * kChunkH;    /* first row of the chunk in the frame */
@@ -229,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, TAILED ? 5 : 0) trace_persistent_ker
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (;;) { /* bulk */
-    unsigned long long c = 0;
-    if (lane == 0) c = atomicAdd(p.next_chunk, 1ull);
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(p.next_chunk, 1u);
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= p.bulk_chunks) break;
     trace_unit<HITS, WALK, false>(p, tab, hmax, &frame_s[warp], stage[warp], c, 0, 4);
@@ -341,7 +346,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   p.vec_store = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0);
   p.chunks_x = (uint32_t)((W + kChunkW - 1) / kChunkW);
   p.chunks_per_frame = (uint32_t)local_tiles * 2u * p.chunks_x;
-  p.total_chunks = (unsigned long long)p.chunks_per_frame * (unsigned long long)n_frames;
+  p.total_chunks = p.chunks_per_frame * (uint32_t)n_frames; /* < 2^31, see frames_per_launch() */
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
   p.hmax_key = &scratch[0].hmax_key;
   p.next_chunk = &scratch[slot].next_chunk;
@@ -368,7 +373,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   const int walk = ctx->trace_variant != 0 ? kWalkReference : (pow2 ? kWalkFastPow2 : kWalkFast);
   /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
   /* tile-granular tail only where it pays: fewer than 64 chunks per resident warp (see the kernel comment) */
-  const bool tailed = p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
+  const bool tailed = (unsigned long long)p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
   const void* fn = pick_kernel(d_hits != nullptr, walk, tailed);
   const int kslot = (tailed ? 6 : 0) + (d_hits ? 3 : 0) + walk;
   if (ctx->ctas_per_sm[kslot] == 0) {
@@ -382,13 +387,17 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
               fa.localSizeBytes, per_sm);
     }
   }
-  const unsigned long long want = (p.total_chunks + kWarps - 1) / kWarps;
+  const unsigned long long want = ((unsigned long long)p.total_chunks + kWarps - 1) / kWarps;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   /* the last "one chunk per resident warp" is distributed tile by tile */
-  unsigned long long tail_chunks = p.total_chunks < (unsigned long long)grid * kWarps ? p.total_chunks : (unsigned long long)grid * kWarps;
+  /* the tail must be long enough to absorb the longest whole chunk claimed just before it (four near-horizon tiles
+   * can take ~10x the mean): 8 chunks per resident warp measured best (1: -4 %, everything tile by tile: -5 %) */
+  const unsigned long long tail_per_warp = getenv("HMRT_TAIL_PER_WARP") ? (unsigned long long)atoll(getenv("HMRT_TAIL_PER_WARP")) : 8ull;
+  unsigned long long tail_chunks = (unsigned long long)grid * kWarps * tail_per_warp;
+  if (tail_chunks > p.total_chunks) tail_chunks = p.total_chunks;
   if (!tailed) tail_chunks = 0;
-  p.bulk_chunks = p.total_chunks - tail_chunks;
+  p.bulk_chunks = (uint32_t)(p.total_chunks - tail_chunks);
   p.tail_tiles = (uint32_t)(tail_chunks * 4ull);
   void* args[] = {&p};
   HMRT_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
@@ -400,14 +409,31 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
 
 extern "C" {
 
+/* frames one launch may carry so that its chunk indices stay below 2^31 */
+static int frames_per_launch(int W, int H) {
+  const unsigned long long per_frame = (unsigned long long)((H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE) * 2ull * (unsigned long long)((W + 31) / 32);
+  const unsigned long long n = per_frame ? (1ull << 31) / per_frame : 1ull;
+  return n < 1 ? 1 : (n > 65535 ? 65535 : (int)n);
+}
+
 int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
                const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits) {
   int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
   if (rc) return rc;
   hmrt::DeviceGuard guard(ctx->device);
-  rc = hmrt::prepare_trace(ctx, 1);
+  const int per = frames_per_launch(W, H);
+  const int n_launches = (n_frames + per - 1) / per;
+  rc = hmrt::prepare_trace(ctx, n_launches);
   if (rc) return rc;
-  return hmrt::launch_trace(ctx, ctx->stream, 0, 0, W, H, h_cameras, n_frames, opts, d_rgb, d_hits);
+  const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
+  const size_t frame_px = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W;
+  for (int l = 0; l < n_launches; ++l) {
+    const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
+    rc = hmrt::launch_trace(ctx, ctx->stream, l, 0, W, H, h_cameras + f0, nf, opts, d_rgb ? d_rgb + (size_t)f0 * frame_px * 3 : nullptr,
+                            d_hits ? d_hits + (size_t)f0 * frame_px : nullptr);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
