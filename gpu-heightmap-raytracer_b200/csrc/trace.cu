@@ -50,6 +50,7 @@ struct TraceParams {
   int rows_local;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
+  PixelGrid pixel_grid; /* (W - 1), (H - 1), their reciprocals; whether the frames allow primary_ray_fast */
   const uint32_t* hmax_key;          /* &scratch[0].hmax_key */
   uint32_t* next_chunk;              /* this launch's work counter (whole chunks) */
   uint32_t* next_tail;               /* ... and the counter of the tile-granular tail */
@@ -164,9 +165,9 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
     if (px < p.W && py < p.H) {
       RayResult r;
       if (WALK == kWalkFastPow2)
-        r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+        r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
       else if (WALK == kWalkFast)
-        r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.W, p.H, px, py);
+        r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
       else
         r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
       stage[ly][tx * 3 + 0] = r.r;
@@ -217,8 +218,11 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
  * launches of hmrt_trace_host, 1/8 frames on 8 GPUs).  TAILED = false compiles the tail out: for launches
  * with hundreds of chunks per warp the tail is irrelevant and the leaner code is ~1.5 % faster (measured).
  */
+#ifndef HMRT_MIN_CTAS
+#define HMRT_MIN_CTAS (TAILED ? 5 : 0)
+#endif
 template <bool HITS, int WALK, bool TAILED>
-__global__ void __launch_bounds__(kThreads, TAILED ? 5 : 0) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(kThreads, HMRT_MIN_CTAS) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kWarps][kChunkH][kStageRow];
   __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
   __shared__ __align__(16) FrameConsts frame_s[kWarps]; /* the frame constants of each warp's current unit */
@@ -351,6 +355,17 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   p.hmax_key = &scratch[0].hmax_key;
   p.next_chunk = &scratch[slot].next_chunk;
   p.next_tail = &scratch[slot].next_tail;
+
+  p.pixel_grid.wm1 = (float)(W - 1);
+  p.pixel_grid.hm1 = (float)(H - 1);
+  p.pixel_grid.rw1 = 1.0f / p.pixel_grid.wm1; /* IEEE single division: the correctly rounded reciprocal div_by needs */
+  p.pixel_grid.rh1 = 1.0f / p.pixel_grid.hm1;
+  p.pixel_grid.fast = 1;
+  for (int i = 0; i < n_frames; ++i)
+    for (int a = 0; a < 2; ++a) {
+      const float m = fabsf(cams[i].frame_dim[a]);
+      if (!(m >= 9.094947017729282e-13f && m <= 1.099511627776e12f)) p.pixel_grid.fast = 0; /* 2^-40 .. 2^40; NaN fails too */
+    }
 
   if (n_frames <= kInlineFrames) {
     for (int i = 0; i < n_frames; ++i) make_frame_consts(cams[i], p.frame_inline[i]);

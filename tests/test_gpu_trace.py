@@ -216,3 +216,25 @@ def test_full_size_4k_over_16384(cuda_ctx):
         for r0_, r1_ in [(0, 4), (1077, 1083), (2156, 2160)]:
             ergb, ehits = _oracle(sc, W, H, cam, opts, rows=(r0_, r1_))
             ol.assert_same_trace((whole[f][r0_:r1_], hits[f][r0_:r1_]), (ergb[r0_:r1_], ehits[r0_:r1_]), f"4K cam{f} rows {r0_}")
+
+
+def test_rcp_inrange_exhaustive():
+    """The production walk's reciprocal (hmrt::rcp_rn_inrange: MUFU.RCP + one Newton step, no range test) has the bits of
+    __frcp_rn for EVERY float with 2^-40 <= |d| <= 2, the range fast_div_ok admits (tests/cuda/rcpcheck.cu)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    here = Path(__file__).resolve().parent
+    exe = here / "_build" / "rcpcheck"
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if Path(nvcc).exists():
+        (here / "_build").mkdir(exist_ok=True)
+        subprocess.run([nvcc, "-O3", "-gencode", "arch=compute_100a,code=sm_100a", str(here / "cuda" / "rcpcheck.cu"), "-o", str(exe)],
+                       check=True, cwd=here / "cuda")
+    assert exe.exists(), "tests/_build/rcpcheck is missing and nvcc is not available to build it"
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches vs __frcp_rn: 0" in out.stdout

@@ -52,6 +52,16 @@ def test_packed_walk_is_not_contracted(sass):
         assert ffma2 == 3 * floor_rm, f"{name}: {ffma2} FFMA2 for {floor_rm} walk steps -- a packed mul/add pair was contracted"
         assert any(i.startswith("FMUL2") for i in ins) and any(i.startswith("FADD2") for i in ins)
         assert not any(re.match(r"D(FMA|ADD|MUL)\b", i) for i in ins), f"{name}: fp64 arithmetic on the traced path"
+    # the air loop of the production kernel: four steps per trip, no register copies, no constant-bank loads
+    for name, ins in prod.items():
+        if "ILb0E" not in name:
+            continue  # the instrumented (hits) variants also count iterations inside the loop
+        rm = [k for k, i in enumerate(ins) if i.startswith("FFMA2.RM")]
+        end = next(k for k in range(rm[3], len(ins)) if "BRA" in ins[k])
+        body = [re.sub(r"^@!?U?P\d+\s+", "", i) for i in ins[rm[0]:end + 1]]
+        assert sum(i.startswith("FFMA2") for i in body) == 16, name
+        assert not any(re.match(r"(MOV|IMAD\.MOV|LDC|LDCU)\b", i) for i in body), f"{name}: copies / constant loads inside the air loop"
+        assert len(body) <= 66, f"{name}: {len(body)} instructions per four air steps"
 
 
 def test_mip_kernel_uses_wide_loads_and_shuffles(sass):
