@@ -39,8 +39,8 @@ COARSE = R0 >> (LEVELS - 1)
 W, H = 3840, 2160
 POSES = 16
 FRAME_DIM = (32.0, 18.0, 20.0)  # main.cpp:57
-NCU_DRAM_BYTES_PER_LAUNCH = 2.182693e9 + 0.367081e9  # profiles/ncu_trace_r01_c_persistent.txt (1 GPU, 16 frames per launch)
-NCU_SOURCE = "profiles/ncu_trace_r01_c_persistent.txt"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.225832e9 + 0.377172e9  # profiles/ncu_trace_r01_e.txt (1 GPU, 16 frames per launch): dram__bytes_read.sum + dram__bytes_write.sum
+NCU_SOURCE = "profiles/ncu_trace_r01_e.txt"
 WORKLOAD = f"{R0}^2 heightmap ({LEVELS}-level max-mip pyramid, 1.43 GB), {W}x{H} primary rays + height-ramp shading, {POSES} camera poses per step"
 
 

@@ -405,10 +405,9 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   const unsigned long long want = ((unsigned long long)p.total_chunks + kWarps - 1) / kWarps;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  /* the last "one chunk per resident warp" is distributed tile by tile */
   /* the tail must be long enough to absorb the longest whole chunk claimed just before it (four near-horizon tiles
    * can take ~10x the mean): 8 chunks per resident warp measured best (1: -4 %, everything tile by tile: -5 %) */
-  const unsigned long long tail_per_warp = getenv("HMRT_TAIL_PER_WARP") ? (unsigned long long)atoll(getenv("HMRT_TAIL_PER_WARP")) : 8ull;
+  static const unsigned long long tail_per_warp = getenv("HMRT_TAIL_PER_WARP") ? (unsigned long long)atoll(getenv("HMRT_TAIL_PER_WARP")) : 8ull; /* tuning knob, read once */
   unsigned long long tail_chunks = (unsigned long long)grid * kWarps * tail_per_warp;
   if (tail_chunks > p.total_chunks) tail_chunks = p.total_chunks;
   if (!tailed) tail_chunks = 0;
