@@ -75,6 +75,23 @@ def test_cameras_outside_and_degenerate_directions(cuda_ctx):
     _both(cuda_ctx, sc, 161, 121, cams, ol.make_opts(mh, shadows=True))
 
 
+def test_frame_dimensions_fast_and_fallback_setup(cuda_ctx):
+    """The pixel -> ray set-up divides by (W - 1) and (H - 1) through host reciprocals when every frame_dimension of the
+    launch lies in [2^-40, 2^40], and takes the IEEE divisions otherwise: both must be the reference's bits.  Wide / narrow /
+    negative (mirrored image plane) frame dimensions, one launch mixing an ordinary and an out-of-range camera (the whole
+    launch falls back), and frame sizes whose (W - 1), (H - 1) are not powers of two."""
+    sc = ol.scene("r512_l4", seed=5)
+    mh = sc["max_height"]
+    pos, fwd = (256.3, 1.6 * mh, 250.7), (0.4, -0.5, 0.77)
+    dims = [(32.0, 18.0, 20.0), (3.0, 40.0, 7.0), (-32.0, 18.0, 20.0), (1e-3, 2e-3, 1.5e-3), (5e11, 3e11, 4e11),   # fast path
+            (1e-13, 1e-13, 1e-13), (3e12, 18.0, 20.0)]                                                            # fallback
+    for W, H in ((160, 120), (97, 61)):
+        for fd in dims:
+            _both(cuda_ctx, sc, W, H, [ol.make_camera(pos, fwd, fd)], ol.make_opts(mh, shadows=True))
+        _both(cuda_ctx, sc, W, H, [ol.make_camera(pos, fwd, dims[0]), ol.make_camera(pos, fwd, dims[6]), ol.make_camera(pos, fwd, dims[1])],
+              ol.make_opts(mh))
+
+
 def test_largest_configuration_32768(cuda_ctx):
     """BASELINE configs[4] shape: 32768^2 heightmap (5.73 GB pyramid), 4K, primary + shadow rays.  Sampled rows against
     the CPU oracle at full size; sharded == whole."""
