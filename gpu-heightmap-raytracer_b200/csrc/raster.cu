@@ -26,6 +26,7 @@ constexpr int kScatterThreads = 256;
 struct ScatterParams {
   double scale[3], offset[3], mn[3];
   float cell[3];
+  float rcell[3]; /* 1 / cell when cell is a power of two (x / 2^k == x * 2^-k bit for bit, one rounding of the same value), else 0 */
   float origin[2];
   int res0;
   int cls_off; /* byte offset of the classification byte, -1: none */
@@ -37,13 +38,39 @@ __device__ __forceinline__ uint32_t color16(uint32_t c) {
   return (uint32_t)__float2int_rz(floorf(__fmul_rn(__fdiv_rn((float)c, 65535.0f), 255.0f))) & 0xffu;
 }
 
+/* x / cell; a power-of-two cell size (launch-uniform) makes it one multiplication */
+__device__ __forceinline__ float div_cell(float x, float cell, float rcell) {
+  return rcell != 0.0f ? __fmul_rn(x, rcell) : __fdiv_rn(x, cell);
+}
+
+/* The first 16 bytes of a LAS point record -- X, Y, Z (int32 LE), intensity, flags, classification -- from five aligned
+ * 32-bit loads and funnel shifts, whatever the record's alignment (26- and 34-byte records alternate between 0 and 2 mod 4):
+ * 5 loads instead of 13 byte loads and their shifts.  Reads at most the 3 bytes in front of the record inside its first
+ * aligned word and never past byte 19 of the record (record_len >= 20). */
+struct RecordHead {
+  int32_t x, y, z;
+  uint32_t tail; /* intensity | flags << 16 | classification << 24 */
+};
+__device__ __forceinline__ RecordHead load_record_head(const uint8_t* rec) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(rec);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  RecordHead h;
+  h.x = (int32_t)__funnelshift_r(w0, w1, sh);
+  h.y = (int32_t)__funnelshift_r(w1, w2, sh);
+  h.z = (int32_t)__funnelshift_r(w2, w3, sh);
+  h.tail = __funnelshift_r(w3, w4, sh);
+  return h;
+}
+
 /* main.cpp:200-209 for one decoded point (gx, gy, gz = liblas Point::GetX/Y/Z in double): finest cell and
  * height, or false when the point is rejected (outside the section, class 7). */
 __device__ __forceinline__ bool point_to_cell(const ScatterParams& sp, double gx, double gy, double gz, int cls, uint32_t& cell,
                                               float& fZ, uint32_t* cx_out = nullptr, uint32_t* cy_out = nullptr) {
-  const float fX = __fdiv_rn(__double2float_rn(__dsub_rn(gx, sp.mn[0])), sp.cell[0]); /* :200 */
-  const float fY = __fdiv_rn(__double2float_rn(__dsub_rn(gy, sp.mn[1])), sp.cell[1]); /* :201 */
-  fZ = __fdiv_rn(__double2float_rn(__dsub_rn(gz, sp.mn[2])), sp.cell[2]);             /* :202 */
+  const float fX = div_cell(__double2float_rn(__dsub_rn(gx, sp.mn[0])), sp.cell[0], sp.rcell[0]); /* :200 */
+  const float fY = div_cell(__double2float_rn(__dsub_rn(gy, sp.mn[1])), sp.cell[1], sp.rcell[1]); /* :201 */
+  fZ = div_cell(__double2float_rn(__dsub_rn(gz, sp.mn[2])), sp.cell[2], sp.rcell[2]);             /* :202 */
   const float dx = floorf(__fsub_rn(fX, sp.origin[0]));                               /* :205 */
   const float dy = floorf(__fsub_rn(fY, sp.origin[1]));                               /* :206 */
   const float r0 = (float)sp.res0;
@@ -66,10 +93,6 @@ __device__ __forceinline__ void bin_point(const ScatterParams& sp, double gx, do
   /* :227-233.  Negative or NaN heights never replace the +0 floor in the reference (`buf <= fZ` is
    * false), -0.0f maps to INT_MIN and is a no-op here. */
   if (fZ >= 0.0f) atomicMax(finest + cell, __float_as_int(fZ));
-}
-
-__device__ __forceinline__ int32_t ld_i32_bytes(const uint8_t* p) {
-  return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
 }
 
 /*
@@ -100,10 +123,11 @@ scatter_las_kernel(const uint8_t* __restrict__ records, int64_t n, int record_le
   }
   if (i >= n) return;
   /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
-  const double gx = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec), sp.scale[0]), sp.offset[0]);
-  const double gy = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 4), sp.scale[1]), sp.offset[1]);
-  const double gz = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 8), sp.scale[2]), sp.offset[2]);
-  const int cls = sp.cls_off >= 0 ? (rec[sp.cls_off] & 0x1f) : 0; /* Classification::GetClass() */
+  const RecordHead rh = load_record_head(rec);
+  const double gx = __dadd_rn(__dmul_rn((double)rh.x, sp.scale[0]), sp.offset[0]);
+  const double gy = __dadd_rn(__dmul_rn((double)rh.y, sp.scale[1]), sp.offset[1]);
+  const double gz = __dadd_rn(__dmul_rn((double)rh.z, sp.scale[2]), sp.offset[2]);
+  const int cls = sp.cls_off == 15 ? (int)((rh.tail >> 24) & 0x1f) : 0; /* Classification::GetClass(): low 5 bits of byte 15 */
   uint32_t rgb = 0;
   if (keys && sp.rgb_off >= 0) {
     const uint8_t* c = rec + sp.rgb_off;
@@ -185,10 +209,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_points_kernel(const __grid_co
       slot[k] = 0xffffffffu;
       if (i < p.n) {
         const uint8_t* rec = p.records + i * p.record_len;
-        const double gx = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec), p.sp.scale[0]), p.sp.offset[0]);
-        const double gy = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 4), p.sp.scale[1]), p.sp.offset[1]);
-        const double gz = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 8), p.sp.scale[2]), p.sp.offset[2]);
-        const int cls = rec[p.sp.cls_off] & 0x1f;
+        const RecordHead rh = load_record_head(rec);
+        const double gx = __dadd_rn(__dmul_rn((double)rh.x, p.sp.scale[0]), p.sp.offset[0]);
+        const double gy = __dadd_rn(__dmul_rn((double)rh.y, p.sp.scale[1]), p.sp.offset[1]);
+        const double gz = __dadd_rn(__dmul_rn((double)rh.z, p.sp.scale[2]), p.sp.offset[2]);
+        const int cls = (int)((rh.tail >> 24) & 0x1f);
         uint32_t cx, cy;
         float fZ;
         if (point_to_cell(p.sp, gx, gy, gz, cls, cell[k], fZ, &cx, &cy) && fZ >= 0.0f) {
@@ -257,6 +282,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_points_kernel(const __grid_co
   for (int t = threadIdx.x; t < p.n_tiles; t += kBinThreads) p.counts[(size_t)t * n_ctas + blockIdx.x] = fill[t];
 }
 
+/* Pass 2.  Every thread keeps four 16-byte loads (eight pairs) in flight before it issues their RED.MAXes: with one 8-byte
+ * load per thread and trip the kernel sat at 29 % of the DRAM rate waiting on its own loads (ncu r01: 347 warps stalled on
+ * long_scoreboard per issue).  Slices start 32-byte aligned (slice_cap % 4 == 0). */
 __global__ void __launch_bounds__(kBinThreads) apply_bins_kernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ counts,
                                                                   uint32_t slice_cap, uint32_t n_ctas, uint32_t groups_per_tile,
                                                                   int* __restrict__ finest) {
@@ -264,8 +292,25 @@ __global__ void __launch_bounds__(kBinThreads) apply_bins_kernel(const uint2* __
   for (uint32_t s = g * kSlicesPerApplyCta; s < min(n_ctas, (g + 1) * kSlicesPerApplyCta); ++s) {
     const uint32_t count = __ldg(counts + (size_t)tile * n_ctas + s);
     const uint2* src = pairs + ((size_t)tile * n_ctas + s) * slice_cap;
-    for (uint32_t i = threadIdx.x; i < count; i += kBinThreads) {
-      const uint2 v = __ldg(src + i);
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    const uint32_t n4 = count >> 1; /* whole 16-byte pieces */
+    for (uint32_t i = threadIdx.x; i < n4; i += kBinThreads * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t j = i + (uint32_t)k * kBinThreads;
+        v[k] = j < n4 ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u); /* (cell 0, +0.0f) is a no-op: heights are >= +0 */
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i + (uint32_t)k * kBinThreads < n4) {
+          atomicMax(finest + v[k].x, (int)v[k].y);
+          atomicMax(finest + v[k].z, (int)v[k].w);
+        }
+      }
+    }
+    if ((count & 1u) && threadIdx.x == 0) {
+      const uint2 v = __ldcs(src + (count - 1));
       atomicMax(finest + v.x, (int)v.y);
     }
   }
@@ -285,8 +330,9 @@ __global__ void __launch_bounds__(256) locality_probe_kernel(const uint8_t* __re
   const int64_t i = start + (int64_t)j * span / kProbeSamples;
   if (i >= n) return;
   const uint8_t* rec = records + i * record_len;
-  const double gx = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec), sp.scale[0]), sp.offset[0]);
-  const double gy = __dadd_rn(__dmul_rn((double)ld_i32_bytes(rec + 4), sp.scale[1]), sp.offset[1]);
+  const RecordHead rh = load_record_head(rec);
+  const double gx = __dadd_rn(__dmul_rn((double)rh.x, sp.scale[0]), sp.offset[0]);
+  const double gy = __dadd_rn(__dmul_rn((double)rh.y, sp.scale[1]), sp.offset[1]);
   uint32_t cell;
   float fZ;
   if (!point_to_cell(sp, gx, gy, 0.0, 0, cell, fZ)) return;
@@ -438,6 +484,9 @@ static int fill_scatter_params(const hmrt_las_transform* xf, int res0, ScatterPa
     sp.mn[i] = xf->min[i];
     sp.cell[i] = xf->cell_size[i];
     if (!(xf->cell_size[i] > 0.0f)) return HMRT_E_ARG;
+    int e = 0;
+    const bool pow2 = frexpf(xf->cell_size[i], &e) == 0.5f && e > -100 && e < 100; /* the reference's default is 2.0 (main.cpp:62) */
+    sp.rcell[i] = pow2 ? 1.0f / xf->cell_size[i] : 0.0f;
   }
   sp.origin[0] = xf->origin[0];
   sp.origin[1] = xf->origin[1];
