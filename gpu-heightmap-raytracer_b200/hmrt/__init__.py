@@ -12,6 +12,8 @@ from ._abi import (  # noqa: F401
     HmrtError,
     LasTransform,
     TraceOpts,
+    WindowPlacement,
+    WindowSections,
     HMRT_ROW_TILE,
     HIT_HIT,
     HIT_MIRROR_X,
@@ -20,5 +22,5 @@ from ._abi import (  # noqa: F401
     HIT_STEPS_SHIFT,
     load,
 )
-from .context import Context, camera, pyramid_layout, rows_local, trace_opts  # noqa: F401
+from .context import Context, camera, pyramid_layout, rows_local, trace_opts, window_place  # noqa: F401
 from . import las, dist  # noqa: F401

@@ -59,6 +59,15 @@ class LasTransform(C.Structure):  # hmrt_las_transform
     ]
 
 
+class WindowPlacement(C.Structure):  # hmrt_window_placement (preparePointBuffer's host arithmetic, main.cpp:461-516)
+    _fields_ = [("min_x", C.c_int), ("min_y", C.c_int), ("max_x", C.c_int), ("max_y", C.c_int),
+                ("cell_x", C.c_int), ("cell_y", C.c_int), ("camera", C.c_float * 3)]
+
+
+class WindowSections(C.Structure):  # hmrt_window_sections: [x][y], x 0 = left, y 0 = bottom
+    _fields_ = [("d_pyramid", (C.c_void_p * 2) * 2), ("d_color_map", (C.c_void_p * 2) * 2)]
+
+
 # every symbol include/hmrt.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 PROTOTYPES = {
@@ -81,6 +90,8 @@ PROTOTYPES = {
     "hmrt_scatter_xyz": (C.c_int, [_P, _P, C.c_int64, C.POINTER(LasTransform), _P, C.c_int, C.c_int]),
     "hmrt_build_mips": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "hmrt_resolve_colors": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "hmrt_window_place": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(WindowPlacement)]),
+    "hmrt_compose_window": (C.c_int, [_P, C.POINTER(WindowSections), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hmrt_set_trace_variant": (C.c_int, [_P, C.c_int]),
     "hmrt_launch_count": (C.c_int64, [_P]),
 }

@@ -234,3 +234,32 @@ class Context:
         self._bind_stream()
         check(self.lib.hmrt_resolve_colors(self._h, self._dev(color_keys, torch.int64, "color_keys"),
                                            self._dev(color_map, torch.uint8, "color_map"), n_cells), "hmrt_resolve_colors")
+
+    # -- camera window over resident sections ------------------------------------------------
+    def compose_window(self, pyramids, color_maps, coarse_res: int, levels: int, cell_x: int, cell_y: int, out_pyramid,
+                       out_color_map=None):
+        """== the copy loops of preparePointBuffer + copyPointBuffer (main.cpp:516-625) on the device.
+        pyramids / color_maps: [[left-bottom, left-top], [right-bottom, right-top]] CUDA tensors (may alias)."""
+        torch = self._torch
+        secs = _abi.WindowSections()
+        for a in range(2):
+            for b in range(2):
+                secs.d_pyramid[a][b] = self._dev(pyramids[a][b], torch.float32, "section pyramid").value
+                if out_color_map is not None:
+                    secs.d_color_map[a][b] = self._dev(color_maps[a][b], torch.uint8, "section colour map").value
+        self._bind_stream()
+        check(self.lib.hmrt_compose_window(
+            self._h, C.byref(secs), coarse_res, levels, int(cell_x), int(cell_y), self._dev(out_pyramid, torch.float32, "window pyramid"),
+            self._dev(out_color_map, torch.uint8, "window colour map") if out_color_map is not None else None), "hmrt_compose_window")
+
+
+def window_place(camera_position, section_origins, grid: int, coarse_res: int, levels: int) -> "_abi.WindowPlacement":
+    """preparePointBuffer's host arithmetic (main.cpp:461-516); section_origins[i][j] = (x, y) like point_sections_origins."""
+    import numpy as np
+
+    cam = (C.c_float * 3)(*[float(v) for v in camera_position])
+    org = np.ascontiguousarray(np.asarray(section_origins, dtype=np.float32).reshape(grid, grid, 2))
+    out = _abi.WindowPlacement()
+    check(_abi.load().hmrt_window_place(cam, org.ctypes.data_as(C.POINTER(C.c_float)), grid, coarse_res, levels, C.byref(out)),
+          "hmrt_window_place")
+    return out

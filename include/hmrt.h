@@ -193,6 +193,41 @@ int hmrt_build_mips(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int levels)
 int hmrt_resolve_colors(hmrt_ctx* ctx, const uint64_t* d_color_keys, hmrt_color* d_color_map,
                         int64_t n_cells);
 
+/* ---- camera window over resident sections (preparePointBuffer + copyPointBuffer, main.cpp:459-625) ------ */
+
+/*
+ * The reference keeps a grid of sections (each one a pyramid + colour map of its own, main.cpp:256-269) in HOST memory and,
+ * every frame, memcpy's the camera-centred window out of the up-to-four sections it straddles into a host point buffer,
+ * level by level (preparePointBuffer, main.cpp:459-618), then uploads 139.8 MB over PCIe (copyPointBuffer, :620-625).
+ * Here the sections are resident in device memory and the window is composed on the device.
+ *
+ * hmrt_window_place is the host arithmetic of preparePointBuffer (:461-514): which sections the window straddles, the
+ * coarsest-level cell of the lower-left one where the window starts (cell_position, :508) and the camera in window
+ * coordinates (camera_point_buffer, :511-514).  `section_origins` is the reference's point_sections_origins[i][j]
+ * flattened as [(i * grid + j) * 2 + {x, y}].  HMRT_E_ARG when the window leaves the grid (the reference would index out
+ * of bounds; its manageSections keeps the camera inside the inner sections).
+ */
+typedef struct hmrt_window_placement {
+  int min_x, min_y, max_x, max_y; /* section indices (main.cpp:472-502) */
+  int cell_x, cell_y;             /* cell_position at the COARSEST level (main.cpp:508) */
+  float camera[3];                /* camera_point_buffer (main.cpp:511-514) */
+} hmrt_window_placement;
+int hmrt_window_place(const float camera_position[3], const float* section_origins, int grid, int coarse_res, int levels,
+                      hmrt_window_placement* out);
+
+/* The four sections under the window: [0][*] = left (min_x), [1][*] = right (max_x), [*][0] = bottom (min_y),
+ * [*][1] = top (max_y); entries may alias.  Colour maps: all NULL, or one per section. */
+typedef struct hmrt_window_sections {
+  const float* d_pyramid[2][2];
+  const hmrt_color* d_color_map[2][2];
+} hmrt_window_sections;
+
+/* == the copy loops of preparePointBuffer (main.cpp:516-618) + copyPointBuffer (:620-625), on the device: at every level i,
+ * with c = cell << (levels-1-i), window(x, y) = section[x + c.x >= res_i][y + c.y >= res_i]((x + c.x) % res_i, (y + c.y) % res_i);
+ * the colour map likewise at the finest resolution.  d_window_color_map may be NULL.  Asynchronous on the context's stream. */
+int hmrt_compose_window(hmrt_ctx* ctx, const hmrt_window_sections* sections, int coarse_res, int levels, int cell_x, int cell_y,
+                        float* d_window_pyramid, hmrt_color* d_window_color_map);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 
 /* Diagnostic: 0 (default) = production traversal kernel; 1 = the operation-by-operation walk that

@@ -21,6 +21,7 @@
  */
 #include "hmrt_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -518,5 +519,118 @@ int hmrt_oracle_pdg_generate(int n, uint64_t seed, float* out_xyz) {
       out_xyz[k] = (float)i, out_xyz[k + 1] = (float)j, out_xyz[k + 2] = GZ(i, j);
     }
   free(z);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * The camera window over the section grid: preparePointBuffer, main.cpp:459-618, restated loop by loop.
+ * ---------------------------------------------------------------------------------------------- */
+
+int hmrt_oracle_window_place(const float camera_position[3], const float* section_origins, int grid, int coarse_res, int levels,
+                             hmrt_window_placement* out) {
+  if (!camera_position || !section_origins || !out || grid < 1 || coarse_res < 1 || levels < 1) return -1;
+#define ORIGIN(i, j, a) section_origins[((size_t)(i) * grid + (j)) * 2 + (a)]
+  /* glm::pow(2.0f, LOD_levels - 1): float under the original toolchain, and exact either way */
+  const float top = powf(2.0f, (float)(levels - 1));
+  const float off_x = top * (float)coarse_res / 2.0f, off_y = top * (float)coarse_res / 2.0f; /* :465-467 */
+  const float bl_x = camera_position[0] - off_x, bl_y = camera_position[2] - off_y;            /* :469 */
+  const float tr_x = camera_position[0] + off_x - FLT_MIN, tr_y = camera_position[2] + off_y - FLT_MIN; /* :470 */
+  int minX, minY, maxX, maxY;
+  /* :472-502.  `minX < grid` is tested first here: the reference reads origins[grid] before it looks at the index. */
+  minX = 0;
+  while (minX < grid && bl_x > ORIGIN(minX, 0, 0)) minX++;
+  minX--;
+  minY = 0;
+  while (minY < grid && bl_y > ORIGIN(0, minY, 1)) minY++;
+  minY--;
+  maxX = 0;
+  while (maxX < grid && tr_x > ORIGIN(maxX, 0, 0)) maxX++;
+  maxX--;
+  maxY = 0;
+  while (maxY < grid && tr_y > ORIGIN(0, maxY, 1)) maxY++;
+  maxY--;
+  if (minX < 0 || minY < 0 || maxX < 0 || maxY < 0) return -1; /* the reference would index [-1] */
+  const float sp_x = bl_x - ORIGIN(minX, minY, 0), sp_y = bl_y - ORIGIN(minX, minY, 1); /* :509 */
+  const int cell_x = (int)floorf(sp_x / top), cell_y = (int)floorf(sp_y / top);       /* :510 */
+  if (cell_x < 0 || cell_y < 0 || cell_x >= coarse_res || cell_y >= coarse_res) return -1;
+  out->min_x = minX, out->min_y = minY, out->max_x = maxX, out->max_y = maxY;
+  out->cell_x = cell_x, out->cell_y = cell_y;
+  const float half_top = powf(2.0f, (float)(levels - 2));
+  out->camera[0] = (sp_x - cell_x * top) + (coarse_res - 1) * half_top; /* :513-516 */
+  out->camera[1] = camera_position[1];
+  out->camera[2] = (sp_y - cell_y * top) + (coarse_res - 1) * half_top;
+#undef ORIGIN
+  return 0;
+}
+
+/* sections[x][y]: x 0 = minX, 1 = maxX; y 0 = minY, 1 = maxY (host pointers).  colors may be NULL (then out_colors too). */
+int hmrt_oracle_compose_window(const float* const sections[2][2], const hmrt_color* const colors[2][2], int coarse_res, int levels,
+                               int cell_x, int cell_y, float* h_point_buffer, hmrt_color* h_color_map) {
+  int LOD_resolutions[HMRT_MAX_LEVELS];
+  int64_t LOD_indexes[HMRT_MAX_LEVELS];
+  if (hmrt_oracle_pyramid_layout(coarse_res, levels, LOD_resolutions, LOD_indexes, NULL)) return -1;
+  int cpx = cell_x, cpy = cell_y; /* cell_position */
+  int row_index, row_offset;
+  for (int i = levels - 1; i >= 0; i--) { /* :519 */
+    const int R = LOD_resolutions[i];
+    const int64_t I = LOD_indexes[i];
+    /* lower left section, :521-529 */
+    row_offset = 0;
+    for (row_index = cpy; row_index < R; row_index++) {
+      memcpy(h_point_buffer + I + (int64_t)row_offset * R, sections[0][0] + I + cpx + (int64_t)row_index * R, sizeof(float) * (size_t)(R - cpx));
+      row_offset++;
+    }
+    /* bottom right section, :531-541 */
+    row_offset = 0;
+    row_index = cpx == 0 ? R : cpy;
+    for (; row_index < R; row_index++) {
+      memcpy(h_point_buffer + I + (R - cpx) + (int64_t)row_offset * R, sections[1][0] + I + (int64_t)row_index * R, sizeof(float) * (size_t)cpx);
+      row_offset++;
+    }
+    /* top left section, :543-553 */
+    row_offset = 0;
+    row_index = cpy == 0 ? cpy : 0;
+    for (; row_index < cpy; row_index++) {
+      memcpy(h_point_buffer + I + (int64_t)(row_index + R - cpy) * R, sections[0][1] + I + cpx + (int64_t)row_offset * R,
+             sizeof(float) * (size_t)(R - cpx));
+      row_offset++;
+    }
+    /* top right section, :555-565 */
+    row_offset = 0;
+    row_index = (cpy == 0 || cpx == 0) ? cpy : 0;
+    for (; row_index < cpy; row_index++) {
+      memcpy(h_point_buffer + I + (R - cpx) + (int64_t)(row_index + R - cpy) * R, sections[1][1] + I + (int64_t)row_offset * R,
+             sizeof(float) * (size_t)cpx);
+      row_offset++;
+    }
+    if (i > 0) cpx *= 2, cpy *= 2; /* :566-567 */
+  }
+  if (!h_color_map) return 0;
+  if (!colors) return -1;
+  const int R = LOD_resolutions[0];
+  /* colour data, :570-618 (cell_position is now at the finest level) */
+  row_offset = 0;
+  for (row_index = cpy; row_index < R; row_index++) {
+    memcpy(h_color_map + (int64_t)row_offset * R, colors[0][0] + cpx + (int64_t)row_index * R, sizeof(hmrt_color) * (size_t)(R - cpx));
+    row_offset++;
+  }
+  row_offset = 0;
+  row_index = cpx == 0 ? R : cpy;
+  for (; row_index < R; row_index++) {
+    memcpy(h_color_map + (R - cpx) + (int64_t)row_offset * R, colors[1][0] + (int64_t)row_index * R, sizeof(hmrt_color) * (size_t)cpx);
+    row_offset++;
+  }
+  row_offset = 0;
+  row_index = cpy == 0 ? cpy : 0;
+  for (; row_index < cpy; row_index++) {
+    memcpy(h_color_map + (int64_t)(row_index + R - cpy) * R, colors[0][1] + cpx + (int64_t)row_offset * R, sizeof(hmrt_color) * (size_t)(R - cpx));
+    row_offset++;
+  }
+  row_offset = 0;
+  row_index = (cpy == 0 || cpx == 0) ? cpy : 0;
+  for (; row_index < cpy; row_index++) {
+    memcpy(h_color_map + (R - cpx) + (int64_t)(row_index + R - cpy) * R, colors[1][1] + (int64_t)row_offset * R, sizeof(hmrt_color) * (size_t)cpx);
+    row_offset++;
+  }
   return 0;
 }

@@ -66,6 +66,15 @@ int hmrt_oracle_build_mips(float* pyramid, int coarse_res, int levels);
  */
 int hmrt_oracle_pdg_generate(int n, uint64_t seed, float* out_xyz);
 
+/*
+ * preparePointBuffer (main.cpp:459-618) restated: the host arithmetic (:461-516) and the four memcpy loops per level
+ * (:519-567) + the colour loops (:570-618), on HOST buffers.  sections[x][y]: x 0 = minX, 1 = maxX; y 0 = minY, 1 = maxY.
+ */
+int hmrt_oracle_window_place(const float camera_position[3], const float* section_origins, int grid, int coarse_res, int levels,
+                             hmrt_window_placement* out);
+int hmrt_oracle_compose_window(const float* const sections[2][2], const hmrt_color* const colors[2][2], int coarse_res, int levels,
+                               int cell_x, int cell_y, float* h_point_buffer, hmrt_color* h_color_map);
+
 #ifdef __cplusplus
 }
 #endif

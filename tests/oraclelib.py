@@ -51,6 +51,10 @@ def oracle() -> C.CDLL:
         lib.hmrt_oracle_build_mips.argtypes = [_P, C.c_int, C.c_int]
         lib.hmrt_oracle_pdg_generate.restype = C.c_int
         lib.hmrt_oracle_pdg_generate.argtypes = [C.c_int, C.c_uint64, _P]
+        lib.hmrt_oracle_window_place.restype = C.c_int
+        lib.hmrt_oracle_window_place.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, _P]
+        lib.hmrt_oracle_compose_window.restype = C.c_int
+        lib.hmrt_oracle_compose_window.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]
         _cache["oracle"] = lib
     return _cache["oracle"]
 
@@ -277,3 +281,32 @@ def golden_expected(g, mode, i):
     hmode = "ramp" if mode == "cmap" else mode  # the walk does not depend on the colouring mode
     hits = np.ascontiguousarray(g[f"hits_{hmode}_{i}"]).view(hit_dtype).reshape(int(g["H"]), int(g["W"]))
     return g[f"rgb_{mode}_{i}"], hits
+
+
+# ---- camera window over the section grid (preparePointBuffer, main.cpp:459-618) ------------------------------------
+
+def oracle_window_place(camera_position, origins, grid, coarse_res, levels):
+    """(rc, WindowPlacement) from the restatement of main.cpp:461-516; origins[i][j] = (x, y)."""
+    from hmrt._abi import WindowPlacement
+
+    cam = (C.c_float * 3)(*[float(v) for v in camera_position])
+    org = np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(grid, grid, 2))
+    out = WindowPlacement()
+    rc = oracle().hmrt_oracle_window_place(cam, org.ctypes.data_as(C.POINTER(C.c_float)), grid, coarse_res, levels, C.byref(out))
+    return rc, out
+
+
+def oracle_compose_window(pyramids, colors, coarse_res, levels, cell_x, cell_y):
+    """The four memcpy loops per level of main.cpp:519-618 on host arrays.  pyramids / colors: [[lb, lt], [rb, rt]]
+    (x-major: [0][*] = left sections, [*][0] = bottom sections); colors may be None."""
+    res, idx, total = pyramid_layout(coarse_res, levels)
+    ptrs = (C.c_void_p * 4)(*[pyramids[a][b].ctypes.data for a in range(2) for b in range(2)])
+    out = np.full(total, np.nan, np.float32)
+    out_c, cptrs = None, None
+    if colors is not None:
+        cptrs = (C.c_void_p * 4)(*[colors[a][b].ctypes.data for a in range(2) for b in range(2)])
+        out_c = np.full((res[0], res[0], 3), 7, np.uint8)
+    rc = oracle().hmrt_oracle_compose_window(ptrs, cptrs, coarse_res, levels, cell_x, cell_y, out.ctypes.data,
+                                             out_c.ctypes.data if out_c is not None else None)
+    assert rc == 0
+    return out, out_c
