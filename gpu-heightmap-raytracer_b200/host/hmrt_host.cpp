@@ -285,6 +285,131 @@ int Heightmap::max_height(float* out) const {
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+float SectionLayout::section_size() const { return std::ldexp(1.0f, levels - 1) * (float)coarse_res; }
+
+std::vector<SectionLayout::Load> SectionLayout::initialize(int grid_, int coarse_res_, int levels_, const Vec3& cam) {
+  grid = grid_, coarse_res = coarse_res_, levels = levels_;
+  origin.assign((size_t)grid * grid * 2, 0.0f);
+  tag.assign((size_t)grid * grid, 0);
+  std::vector<Load> loads;
+  const float top = std::ldexp(1.0f, levels - 1);
+  for (int i = 0; i < grid; ++i)
+    for (int j = 0; j < grid; ++j) { /* main.cpp:280-286 */
+      float* o = &origin[((size_t)i * grid + j) * 2];
+      o[0] = cam.x + ((float)i - (float)grid / 2.0f) * top * (float)coarse_res;
+      o[1] = cam.z + ((float)j - (float)grid / 2.0f) * top * (float)coarse_res;
+      tag[(size_t)i * grid + j] = i * grid + j;
+      loads.push_back({i, j, i * grid + j, {o[0], o[1]}});
+    }
+  return loads;
+}
+
+std::vector<SectionLayout::Load> SectionLayout::manage(const Vec3& cam) {
+  std::vector<Load> loads;
+  if (grid < 2) return loads;
+  const float size = section_size();
+  auto org = [&](int i, int j) { return &origin[((size_t)i * grid + j) * 2]; };
+  auto tg = [&](int i, int j) -> int& { return tag[(size_t)i * grid + j]; };
+  auto move = [&](int di, int dj, int si, int sj) { /* point_sections[di][dj] = point_sections[si][sj] etc. (:336-339) */
+    org(di, dj)[0] = org(si, sj)[0], org(di, dj)[1] = org(si, sj)[1];
+    tg(di, dj) = tg(si, sj);
+  };
+  auto place = [&](int i, int j, int t, float ox, float oy) { /* allocateSection (:256-269) on a recycled section object */
+    org(i, j)[0] = ox, org(i, j)[1] = oy;
+    tg(i, j) = t;
+    loads.push_back({i, j, t, {ox, oy}});
+  };
+  std::vector<int> freed((size_t)grid);
+  /* allocate left, move sections right (:410-417) */
+  if (cam.x < org(1, 0)[0]) {
+    for (int j = 0; j < grid; ++j) freed[j] = tg(grid - 1, j); /* unloadSectionsColumn(size - 1) */
+    for (int i = grid - 1; i >= 1; --i)                         /* rearrangeSectionsX(1), :334-345 */
+      for (int j = 0; j < grid; ++j) move(i, j, i - 1, j);
+    for (int j = 0; j < grid; ++j) place(0, j, freed[j], org(1, j)[0] - size, org(1, j)[1]);
+  }
+  /* allocate right, move sections left (:420-427) */
+  if (cam.x >= org(grid - 1, grid - 1)[0]) {
+    for (int j = 0; j < grid; ++j) freed[j] = tg(0, j);
+    for (int i = 0; i < grid - 1; ++i) /* rearrangeSectionsX(-1), :348-361 */
+      for (int j = 0; j < grid; ++j) move(i, j, i + 1, j);
+    for (int j = 0; j < grid; ++j) place(grid - 1, j, freed[j], org(grid - 2, j)[0] + size, org(grid - 2, j)[1]);
+  }
+  /* allocate down, move sections up (:430-437) */
+  if (cam.z < org(0, 1)[1]) {
+    for (int i = 0; i < grid; ++i) freed[i] = tg(i, grid - 1);
+    for (int i = 0; i < grid; ++i) /* rearrangeSectionsY(1), :371-383 */
+      for (int j = grid - 1; j >= 1; --j) move(i, j, i, j - 1);
+    for (int i = 0; i < grid; ++i) place(i, 0, freed[i], org(i, 1)[0], org(i, 1)[1] - size);
+  }
+  /* allocate up, move sections down (:440-447) */
+  if (cam.z >= org(0, grid - 1)[1]) {
+    for (int i = 0; i < grid; ++i) freed[i] = tg(i, 0);
+    for (int i = 0; i < grid; ++i) /* rearrangeSectionsY(-1), :386-399 */
+      for (int j = 0; j < grid - 1; ++j) move(i, j, i, j + 1);
+    for (int i = 0; i < grid; ++i) place(i, grid - 1, freed[i], org(i, grid - 2)[0], org(i, grid - 2)[1] + size);
+  }
+  return loads;
+}
+
+SectionGrid::SectionGrid(hmrt_ctx* ctx, int coarse_res, int levels, int grid, bool with_colors, Loader loader)
+    : ctx_(ctx), coarse_res_(coarse_res), levels_(levels), grid_(grid), loader_(std::move(loader)) {
+  if (grid < 2 || !loader_) {
+    status_ = HMRT_E_ARG;
+    return;
+  }
+  for (int k = 0; k < grid * grid && status_ == 0; ++k) {
+    sections_.emplace_back(new Heightmap(ctx, coarse_res, levels, with_colors));
+    status_ = sections_.back()->status();
+  }
+}
+
+int SectionGrid::fill(const std::vector<SectionLayout::Load>& loads) {
+  int filled = 0;
+  for (size_t k = 0; k < loads.size(); ++k) {
+    const SectionLayout::Load& l = loads[k];
+    bool superseded = false; /* a later shift of the same call recycled this section again: only its last origin counts */
+    for (size_t m = k + 1; m < loads.size(); ++m) superseded |= loads[m].tag == l.tag;
+    if (superseded) continue;
+    ++filled;
+    Heightmap& s = *sections_[(size_t)l.tag];
+    int rc = s.clear(); /* `new float[n]()`, main.cpp:259-260 */
+    if (rc == 0) rc = loader_(s, l.origin);
+    if (rc == 0) rc = s.finish();
+    if (rc) return rc > 0 ? -1000 - rc : rc;
+  }
+  return filled;
+}
+
+int SectionGrid::initialize(const Vec3& cam) {
+  if (status_) return status_;
+  return fill(layout_.initialize(grid_, coarse_res_, levels_, cam));
+}
+
+int SectionGrid::manage(const Vec3& cam) {
+  if (status_) return status_;
+  return fill(layout_.manage(cam));
+}
+
+int SectionGrid::prepare_window(const Vec3& cam, Heightmap& window, Vec3* camera_point_buffer) {
+  if (status_) return status_;
+  const float c[3] = {cam.x, cam.y, cam.z};
+  hmrt_window_placement pl;
+  int rc = hmrt_window_place(c, layout_.origin.data(), grid_, coarse_res_, levels_, &pl);
+  if (rc) return rc;
+  hmrt_window_sections secs;
+  const int xs[2] = {pl.min_x, pl.max_x}, ys[2] = {pl.min_y, pl.max_y};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const Heightmap& s = section(xs[a], ys[b]);
+      secs.d_pyramid[a][b] = s.d_pyramid();
+      secs.d_color_map[a][b] = s.d_color_map();
+    }
+  rc = hmrt_compose_window(ctx_, &secs, coarse_res_, levels_, pl.cell_x, pl.cell_y, window.d_pyramid(), window.d_color_map());
+  if (rc == 0 && camera_point_buffer) *camera_point_buffer = {pl.camera[0], pl.camera[1], pl.camera[2]};
+  return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 static Vec3 normalize(Vec3 v) {
   const float s = 1.0f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
   return {v.x * s, v.y * s, v.z * s};
@@ -409,6 +534,81 @@ void hmrt_host_camera_step(float* state, float fwd, float right, float up, float
   c.rotate(yaw, pitch, dt);
   state[0] = c.position.x, state[1] = c.position.y, state[2] = c.position.z;
   state[3] = c.forward.x, state[4] = c.forward.y, state[5] = c.forward.z;
+}
+
+/* SectionLayout from Python: origins [grid][grid][2] and tags [grid][grid] in / out; loads (i, j, tag) triples out.
+ * init != 0: initializeSections, else manageSections.  Returns the number of loads. */
+int hmrt_host_section_layout_step(int init, int grid, int coarse_res, int levels, const float* cam, float* origins, int* tags,
+                                  int* loads_ijt, float* load_origins, int max_loads) {
+  hmrt_host::SectionLayout L;
+  std::vector<hmrt_host::SectionLayout::Load> loads;
+  const hmrt_host::Vec3 c = {cam[0], cam[1], cam[2]};
+  if (init) {
+    loads = L.initialize(grid, coarse_res, levels, c);
+  } else {
+    L.grid = grid, L.coarse_res = coarse_res, L.levels = levels;
+    L.origin.assign(origins, origins + (size_t)grid * grid * 2);
+    L.tag.assign(tags, tags + (size_t)grid * grid);
+    loads = L.manage(c);
+  }
+  std::memcpy(origins, L.origin.data(), L.origin.size() * sizeof(float));
+  std::memcpy(tags, L.tag.data(), L.tag.size() * sizeof(int));
+  if ((int)loads.size() > max_loads) return HMRT_E_ARG;
+  for (size_t k = 0; k < loads.size(); ++k) {
+    loads_ijt[3 * k] = loads[k].i, loads_ijt[3 * k + 1] = loads[k].j, loads_ijt[3 * k + 2] = loads[k].tag;
+    load_origins[2 * k] = loads[k].origin[0], load_origins[2 * k + 1] = loads[k].origin[1];
+  }
+  return (int)loads.size();
+}
+
+/* End-to-end driver of the section flow for the tests (needs a GPU): a SectionGrid whose loader rasterises one point per
+ * cell with the exactly reproducible height ((wx * 73856093) ^ (wz * 19349663)) & 1023) / 8 at world cell (wx, wz) follows
+ * the camera path cams[0..n) (initializeSections at cams[0], manageSections at every later position), then the window of the
+ * last position is composed.  Out: the window pyramid, camera_point_buffer, the final origins and tags, total sections loaded. */
+int hmrt_host_section_grid_run(int coarse_res, int levels, int grid, const float* cams, int n, float* out_window, float* out_cam_pb,
+                               float* out_origins, int* out_tags, int* out_loaded) {
+  using namespace hmrt_host;
+  if (n < 1) return HMRT_E_ARG;
+  hmrt_ctx* ctx = nullptr;
+  int rc = hmrt_create(0, &ctx);
+  if (rc) return rc;
+  {
+    const PyramidLayout lay(coarse_res, levels);
+    const int r0 = lay.finest();
+    auto loader = [&](Heightmap& sec, const float origin[2]) {
+      std::vector<float> xyz((size_t)r0 * r0 * 3);
+      for (int z = 0; z < r0; ++z)
+        for (int x = 0; x < r0; ++x) {
+          const long long wx = (long long)std::floor(origin[0]) + x, wz = (long long)std::floor(origin[1]) + z;
+          float* p = &xyz[((size_t)z * r0 + x) * 3];
+          p[0] = origin[0] + (float)x + 0.5f, p[1] = origin[1] + (float)z + 0.5f;
+          p[2] = (float)((((unsigned long long)wx * 73856093ull) ^ ((unsigned long long)wz * 19349663ull)) & 1023ull) / 8.0f;
+        }
+      const float cell[3] = {1.f, 1.f, 1.f};
+      return sec.rasterise_xyz(xyz, cell, origin);
+    };
+    SectionGrid sg(ctx, coarse_res, levels, grid, false, loader);
+    Heightmap window(ctx, coarse_res, levels, false);
+    rc = sg.status() ? sg.status() : window.status();
+    int loaded = 0;
+    for (int k = 0; k < n && rc == 0; ++k) {
+      const Vec3 c = {cams[3 * k], cams[3 * k + 1], cams[3 * k + 2]};
+      const int r = k == 0 ? sg.initialize(c) : sg.manage(c);
+      if (r < 0) rc = r; else loaded += r;
+    }
+    Vec3 pb{0, 0, 0};
+    if (rc == 0) rc = sg.prepare_window({cams[3 * (n - 1)], cams[3 * (n - 1) + 1], cams[3 * (n - 1) + 2]}, window, &pb);
+    if (rc == 0) rc = hmrt_synchronize(ctx);
+    if (rc == 0) rc = (int)cudaMemcpy(out_window, window.d_pyramid(), sizeof(float) * (size_t)lay.total, cudaMemcpyDeviceToHost);
+    if (rc == 0) {
+      out_cam_pb[0] = pb.x, out_cam_pb[1] = pb.y, out_cam_pb[2] = pb.z;
+      std::memcpy(out_origins, sg.layout().origin.data(), sg.layout().origin.size() * sizeof(float));
+      std::memcpy(out_tags, sg.layout().tag.data(), sg.layout().tag.size() * sizeof(int));
+      *out_loaded = loaded;
+    }
+  }
+  hmrt_destroy(ctx);
+  return rc;
 }
 
 }  // extern "C"

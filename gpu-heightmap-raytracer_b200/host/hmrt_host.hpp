@@ -14,12 +14,16 @@
  *   moveCamera / rotateCamera           :753-781      Camera::move / Camera::rotate
  *   updateTexture -> CudaSpace::rayTrace :675-690     Renderer::render (device or host framebuffer)
  *   GL PBO + quad                       :635-743      write_ppm (headless; GL is out of scope)
- *
- * The out-of-core section manager and the per-frame window re-upload (main.cpp:256-625) are not
- * mirrored: the whole pyramid stays resident in HBM.
+ *   initializeSections / manageSections :276-448      SectionGrid::initialize / manage (the sections are resident
+ *                                                     DEVICE heightmaps, filled by the GPU rasteriser -- no loader
+ *                                                     threads, no host copies)
+ *   preparePointBuffer + copyPointBuffer :459-625     SectionGrid::prepare_window (hmrt_window_place +
+ *                                                     hmrt_compose_window: a device-side gather, no PCIe upload)
  */
 #pragma once
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -99,6 +103,50 @@ class Heightmap {
   hmrt_color* d_color_map_ = nullptr;
   uint64_t* d_color_keys_ = nullptr;
   uint64_t points_seen_ = 0;
+  int status_ = 0;
+};
+
+/* The origins of the section grid and the reference's shift rules (manageSections, main.cpp:407-448; rearrangeSections*,
+ * :329-402) as pure host logic: `tag[i][j]` identifies which section object sits at (i, j). */
+struct SectionLayout {
+  int grid = 0, coarse_res = 0, levels = 0;
+  std::vector<float> origin; /* [(i * grid + j) * 2 + {x, y}] == point_sections_origins[i][j] */
+  std::vector<int> tag;      /* [i * grid + j] */
+  struct Load {
+    int i, j, tag;   /* the section object `tag`, now at (i, j), must be (re)filled ... */
+    float origin[2]; /* ... for this origin (allocateSection, main.cpp:256-269) */
+  };
+  float section_size() const; /* pow(2, levels - 1) * coarse_res: world extent of a section in cells */
+  /* initializeSections (main.cpp:276-288): grid x grid sections centred on the camera; every section is a Load */
+  std::vector<Load> initialize(int grid, int coarse_res, int levels, const Vec3& camera_position);
+  /* manageSections (main.cpp:407-448): shift the grid when the camera leaves the inner sections; returns the sections to fill */
+  std::vector<Load> manage(const Vec3& camera_position);
+};
+
+/* The section grid resident in device memory + the per-frame camera window. */
+class SectionGrid {
+ public:
+  /* fills one section for an origin: the reference's loadLASToSection(file, origin, ...) (main.cpp:174) */
+  using Loader = std::function<int(Heightmap& section, const float origin[2])>;
+  SectionGrid(hmrt_ctx* ctx, int coarse_res, int levels, int grid, bool with_colors, Loader loader);
+  bool ok() const { return status_ == 0; }
+  int status() const { return status_; }
+  int initialize(const Vec3& camera_position); /* initializeSections */
+  /* manageSections: returns the number of sections (re)loaded, or a negative / CUDA error code */
+  int manage(const Vec3& camera_position);
+  /* preparePointBuffer + copyPointBuffer (main.cpp:459-625): compose the camera-centred window into `window`
+   * (a Heightmap of the same layout) and return camera_point_buffer, the camera in window coordinates */
+  int prepare_window(const Vec3& camera_position, Heightmap& window, Vec3* camera_point_buffer);
+  const SectionLayout& layout() const { return layout_; }
+  const Heightmap& section(int i, int j) const { return *sections_[layout_.tag[(size_t)i * layout_.grid + j]]; }
+
+ private:
+  int fill(const std::vector<SectionLayout::Load>& loads);
+  hmrt_ctx* ctx_;
+  int coarse_res_, levels_, grid_;
+  Loader loader_;
+  SectionLayout layout_;
+  std::vector<std::unique_ptr<Heightmap>> sections_; /* indexed by tag */
   int status_ = 0;
 };
 

@@ -141,3 +141,47 @@ def test_compose_window_default_size_bandwidth(cuda_ctx):
     want, want_c = ol.oracle_compose_window(pyr, col, coarse, levels, 13, 22)
     assert (out.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all() and (out_c.cpu().numpy() == want_c).all()
     assert ms < 1.0, f"compose_window took {ms:.3f} ms"
+
+
+def test_section_grid_follows_camera_and_composes_window():
+    """C++ host layer end to end (hmrt_host::SectionGrid): initializeSections at the first camera, manageSections along a
+    walk that crosses section borders in both axes, GPU rasterisation of every (re)loaded section, then the window of the
+    last camera -- against numpy sections + the oracle's preparePointBuffer restatement."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    host = Path(__file__).resolve().parent.parent / "gpu-heightmap-raytracer_b200" / "host"
+    subprocess.run(["make", "-s", "-C", str(host), "libhmrt_host.so"], check=True)
+    lib = C.CDLL(str(host / "libhmrt_host.so"))
+    lib.hmrt_host_section_grid_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    coarse, levels, grid = 8, 5, 4
+    size = coarse << (levels - 1)
+    res, idx, total = ol.pyramid_layout(coarse, levels)
+    # steps shorter than a section (128 cells): manageSections shifts by one section per call, like the reference per frame
+    cams = np.array([[4000.0, 60.0, 9000.0], [4100.0, 60.0, 9050.0], [4200.0, 60.0, 8950.0], [4300.0, 60.0, 8850.0], [4290.5, 61.0, 8750.25],
+                     [4200.0, 61.0, 8650.0], [4100.0, 50.0, 8661.0], [4003.0, 50.0, 8661.0], [3921.75, 50.0, 8661.5]], np.float32)
+    win = np.zeros(total, np.float32)
+    pb = np.zeros(3, np.float32)
+    origins = np.zeros((grid, grid, 2), np.float32)
+    tags = np.zeros((grid, grid), np.int32)
+    loaded = C.c_int(0)
+    rc = lib.hmrt_host_section_grid_run(coarse, levels, grid, cams.ctypes.data, len(cams), win.ctypes.data, pb.ctypes.data,
+                                        origins.ctypes.data, tags.ctypes.data, C.byref(loaded))
+    assert rc == 0
+    assert loaded.value > grid * grid  # the walk forced reloads
+    rc, pl = ol.oracle_window_place(cams[-1], origins, grid, coarse, levels)
+    assert rc == 0 and np.array_equal(np.array(pl.camera, np.float32), pb)
+
+    def section(i, j):
+        ox, oz = int(np.floor(origins[i, j, 0])), int(np.floor(origins[i, j, 1]))
+        wx = (ox + np.arange(size, dtype=np.int64))[None, :].astype(np.uint64)
+        wz = (oz + np.arange(size, dtype=np.int64))[:, None].astype(np.uint64)
+        fin = (((wx * np.uint64(73856093)) ^ (wz * np.uint64(19349663))) & np.uint64(1023)).astype(np.float32) / np.float32(8.0)
+        return ol.pyramid_from_finest(fin, levels)
+
+    secs = [[section(pl.min_x, pl.min_y), section(pl.min_x, pl.max_y)], [section(pl.max_x, pl.min_y), section(pl.max_x, pl.max_y)]]
+    want, _ = ol.oracle_compose_window(secs, None, coarse, levels, pl.cell_x, pl.cell_y)
+    assert (win.view(np.uint32) == want.view(np.uint32)).all()
