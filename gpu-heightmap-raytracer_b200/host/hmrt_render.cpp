@@ -6,6 +6,7 @@
  *   hmrt_render --generate 1024 --seed 7 --width 640 --height 480 --out frame        (BASELINE config 1 input)
  *   hmrt_render --las ../Data/autzen.las --width 1920 --height 1080 --frames 8 --shadows --out fly
  *   hmrt_render --pdg ../Data/data --grid 1024 --out terrain
+ *   hmrt_render --las cloud.las --sections 4 --coarse 32 --frames 8 --out win       (the reference's section grid + window)
  */
 #include <chrono>
 #include <cstdio>
@@ -25,7 +26,7 @@ static int die(const char* what, int code) {
 
 int main(int argc, char** argv) {
   std::string las_path, pdg_path, out = "frame";
-  int generate = 0, grid = 0, levels = 8, width = 640, height = 480, frames = 1, device = 0;
+  int generate = 0, grid = 0, levels = 8, width = 640, height = 480, frames = 1, device = 0, sections = 0, coarse_arg = 32;
   uint64_t seed = 1;
   bool shadows = false, colors = false;
   for (int i = 1; i < argc; ++i) {
@@ -40,12 +41,15 @@ int main(int argc, char** argv) {
     else if (arg("--height")) height = std::atoi(argv[++i]);
     else if (arg("--frames")) frames = std::atoi(argv[++i]);
     else if (arg("--device")) device = std::atoi(argv[++i]);
+    else if (arg("--sections")) sections = std::atoi(argv[++i]);
+    else if (arg("--coarse")) coarse_arg = std::atoi(argv[++i]);
     else if (arg("--out")) out = argv[++i];
     else if (std::strcmp(argv[i], "--shadows") == 0) shadows = true;
     else if (std::strcmp(argv[i], "--colors") == 0) colors = true;
     else {
       std::fprintf(stderr, "usage: hmrt_render (--las F | --pdg F --grid N | --generate N [--seed S]) [--levels L] [--width W] [--height H] "
-                           "[--frames N] [--shadows] [--colors] [--device D] [--out PREFIX]\n");
+                           "[--frames N] [--shadows] [--colors] [--device D] [--out PREFIX] [--sections G --coarse C  (LAS only: G x G resident sections of "
+                           "C * 2^(L-1) cells around the camera, one window per frame, main.cpp:276-625)]\n");
       return 2;
     }
   }
@@ -85,6 +89,53 @@ int main(int argc, char** argv) {
     cell[0] = cell[1] = cell[2] = 1.f;
     scene.boundaries[0] = scene.boundaries[1] = (float)r0;
   }
+  /* ---- the reference's own flow: a grid of sections around the camera, one composed window per frame (main.cpp:947-966) ---- */
+  if (sections > 0) {
+    if (las_path.empty()) return die("--sections needs --las", HMRT_E_ARG);
+    SectionGrid sg(ctx, coarse_arg, levels, sections, colors, [&](Heightmap& sec, const float org[2]) {
+      return sec.rasterise_las(las, scene.cell_size, org); /* loadLASToSection(file, origin, ...), main.cpp:174 */
+    });
+    if (!sg.ok()) return die("SectionGrid", sg.status());
+    Heightmap window(ctx, coarse_arg, levels, colors); /* d_point_buffer + d_color_map, main.cpp:1012-1013 */
+    if (!window.ok()) return die("window", window.status());
+    Camera cam;
+    cam.position = scene.camera_position;
+    rc = sg.initialize(cam.position);
+    if (rc < 0) return die("initializeSections", rc);
+    std::printf("%d x %d sections of %d^2 cells loaded\n", sections, sections, window.layout().finest());
+    Renderer renderer(ctx, width, height);
+    hmrt_trace_opts opts;
+    hmrt_trace_opts_default(&opts, scene.max_height);
+    opts.use_color_map = colors ? 1 : 0;
+    opts.shadows = shadows ? 1 : 0;
+    opts.light_dir[0] = 0.3244f, opts.light_dir[1] = 0.8111f, opts.light_dir[2] = 0.4867f;
+    std::vector<uint8_t> rgb;
+    for (int f = 0; f < frames; ++f) {
+      const auto f0 = std::chrono::steady_clock::now();
+      rc = sg.manage(cam.position); /* manageSections */
+      if (rc < 0) return die("manageSections", rc);
+      const int reloaded = rc;
+      Camera wc = cam; /* camera_point_buffer: the camera in window coordinates */
+      rc = sg.prepare_window(cam.position, window, &wc.position); /* preparePointBuffer + copyPointBuffer */
+      if (rc) return die("preparePointBuffer", rc);
+      rc = renderer.set_heightmap(window, scene.max_height);
+      if (rc == 0) rc = renderer.render(wc, opts);
+      if (rc) return die("rayTrace", rc);
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
+      rc = renderer.download(rgb);
+      if (rc) return die("download", rc);
+      char name[512];
+      std::snprintf(name, sizeof name, "%s_%04d.ppm", out.c_str(), f);
+      if (!write_ppm(name, rgb.data(), width, height)) return die("write_ppm", HMRT_E_ARG);
+      std::printf("FPS: %.1f  Pos: %.1f %.1f %.1f  window %.1f %.1f  sections reloaded %d -> %s\n", 1.0 / dt, cam.position.x, cam.position.y,
+                  cam.position.z, wc.position.x, wc.position.z, reloaded, name);
+      cam.move(250.f, 0.f, 0.f, 0.1f, scene.boundaries, scene.max_height);
+      cam.rotate(1.f, 0.f, 0.1f);
+    }
+    hmrt_destroy(ctx);
+    return 0;
+  }
+
   if (r0 % (1 << (levels - 1))) return die("grid size must be a multiple of 2^(levels-1)", HMRT_E_SHAPE);
   const int coarse = r0 >> (levels - 1);
 

@@ -83,3 +83,36 @@ def test_las_file_to_frames(tmp_path):
     opts = ol.make_opts(float(mh), use_color_map=True)
     want, _ = ol.cpu_trace(ol.oracle().hmrt_oracle_trace, pyr, cmap, r0 >> 7, 8, W, H, cam, opts)
     assert (got == want).all()
+
+
+def test_las_section_grid_window_frames(tmp_path):
+    """The reference's own main loop (main.cpp:947-966) headless: 4 x 4 resident sections around the camera, manageSections,
+    one composed window per frame, rayTrace in window coordinates -- frame 0 against the same flow on the CPU oracle."""
+    import hmrt
+
+    hdr, rec = rl.synthetic_las(400_000, 512, seed=12, frac_outside=0.0)
+    path = tmp_path / "cloud.las"
+    las.write_las(path, hdr, rec)
+    W, H, coarse, levels, grid = 128, 96, 1, 8, 4  # sections of 128^2 cells
+    out = _cli("--las", path, "--sections", grid, "--coarse", coarse, "--levels", levels, "--width", W, "--height", H, "--frames", 3,
+               "--colors", "--out", tmp_path / "s")
+    assert "sections of 128^2 cells loaded" in out and (tmp_path / "s_0002.ppm").exists()
+    got = _read_ppm(tmp_path / "s_0000.ppm")
+    size = coarse << (levels - 1)
+    X0, Y0 = int(rec[0, 0:4].view("<i4")[0]), int(rec[0, 4:8].view("<i4")[0])
+    mh = np.float32(np.float32(hdr.max[2] - hdr.min[2]) / np.float32(2.0))
+    cam_world = (np.float32(((X0 * hdr.scale[0] + hdr.offset[0]) - hdr.min[0]) / 2.0), np.float32((hdr.max[2] - hdr.min[2]) / 2.0),
+                 np.float32(((Y0 * hdr.scale[1] + hdr.offset[1]) - hdr.min[1]) / 2.0))
+    org = np.array([[[np.float32(cam_world[0] + np.float32((i - grid / 2.0) * size)), np.float32(cam_world[2] + np.float32((j - grid / 2.0) * size))]
+                     for j in range(grid)] for i in range(grid)], np.float32)  # initializeSections, main.cpp:276-288
+    rc, pl = ol.oracle_window_place(cam_world, org, grid, coarse, levels)
+    assert rc == 0
+    sec = {(i, j): rl.oracle_rasterise(hdr, rec, coarse, levels, origin=tuple(org[i, j])) for i in {pl.min_x, pl.max_x} for j in {pl.min_y, pl.max_y}}
+    pick = lambda k: [[sec[pl.min_x, pl.min_y][k], sec[pl.min_x, pl.max_y][k]], [sec[pl.max_x, pl.min_y][k], sec[pl.max_x, pl.max_y][k]]]  # noqa: E731
+    win, wcol = ol.oracle_compose_window(pick(0), pick(1), coarse, levels, pl.cell_x, pl.cell_y)
+    cam = ol.Camera()
+    cam.frame_dim[:] = [32.0, 18.0, 20.0]
+    cam.forward[:] = [0.0, float(np.float32(-0.6689647)), float(np.float32(0.7432941))]
+    cam.position[:] = list(pl.camera)
+    want, _ = ol.cpu_trace(ol.oracle().hmrt_oracle_trace, win, wcol, coarse, levels, W, H, cam, ol.make_opts(float(mh), use_color_map=True))
+    assert (got == want).all()
