@@ -12,6 +12,7 @@ import argparse
 import json
 import os
 import sys
+import time
 from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
@@ -56,6 +57,7 @@ def main():
     ap.add_argument("--order", default="random", choices=["random", "swath"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 direct atomics, 2 tile-binned")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="points of the CPU baseline sample (0 = skip)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -100,8 +102,28 @@ def main():
         peak = float(json.loads(pk.read_text())["hbm_gbs"])
     scatter_bytes = n * (rec_len + 4)
     mip_bytes = 4 * R0 * R0 * 4 / 3
+    # CPU baseline (reported, not a target): the restated loadLASToSection loop (main.cpp:193-234, all levels
+    # with the early-break max propagation) on ONE host core over the first --cpu-sample points of this workload
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        sys.path.insert(0, str(REPO / "tests"))
+        import ctypes as C
+
+        import numpy as np
+        import oraclelib as ol
+
+        k = min(n, args.cpu_sample)
+        host_rec = rec[:k].cpu().numpy()
+        host_pyr = np.zeros(total, np.float32)
+        t0 = time.perf_counter()
+        rc = ol.oracle().hmrt_oracle_rasterise_las(host_rec.ctypes.data, k, rec_len, args.format, C.byref(xf), host_pyr.ctypes.data, COARSE, LEVELS, None)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        cpu = {"value": k / dt / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+               "sample": f"first {k} points of the workload through the restated main.cpp:193-234 loop (all 8 levels), {dt:.1f} s"}
     if rank == 0:
         print(json.dumps({
+            "cpu_baseline": cpu,
             "workload": f"{args.points} LAS format-{args.format} points ({args.order} order) -> {R0}^2 grid, {world} GPU(s), scatter mode {args.mode}",
             "scatter": {"ms": scatter_ms, "Mpoints_per_s_total": args.points / scatter_ms / 1e3, "algorithmic_GBps_per_gpu": scatter_bytes / scatter_ms / 1e6,
                         "roofline_frac": scatter_bytes / scatter_ms / 1e6 / peak},
