@@ -48,6 +48,7 @@ const char* hmrt_error_string(int code) {
     case HMRT_E_STATE: return "invalid call order (no heightmap set)";
     case HMRT_E_SHAPE: return "unsupported grid shape";
     case HMRT_E_NOMEM: return "host allocation failed";
+    case HMRT_E_NCCL: return "NCCL unavailable or a NCCL call failed";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -21,7 +21,7 @@ HIT_MIRROR_Z = 4
 HIT_SHADOWED = 8
 HIT_STEPS_SHIFT = 8
 
-E_ARG, E_STATE, E_SHAPE, E_NOMEM = -1, -2, -3, -4
+E_ARG, E_STATE, E_SHAPE, E_NOMEM, E_NCCL = -1, -2, -3, -4, -5
 
 
 class Color(C.Structure):  # hmrt_color == CudaSpace::Color (CudaKernel.cuh:37-48)
@@ -92,6 +92,8 @@ PROTOTYPES = {
     "hmrt_resolve_colors": (C.c_int, [_P, _P, _P, C.c_int64]),
     "hmrt_window_place": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(WindowPlacement)]),
     "hmrt_compose_window": (C.c_int, [_P, C.POINTER(WindowSections), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hmrt_broadcast_heightmap": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "hmrt_allreduce_max_heights": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
     "hmrt_set_trace_variant": (C.c_int, [_P, C.c_int]),
     "hmrt_launch_count": (C.c_int64, [_P]),
 }

@@ -38,6 +38,7 @@ extern "C" {
 #define HMRT_E_STATE (-2)    /* call order: e.g. trace before set_heightmap */
 #define HMRT_E_SHAPE (-3)    /* grid does not tile / too large for 32-bit cell indices */
 #define HMRT_E_NOMEM (-4)    /* host allocation failed */
+#define HMRT_E_NCCL (-5)     /* NCCL missing (libnccl.so.2 not loadable) or a NCCL call failed */
 
 typedef struct hmrt_ctx hmrt_ctx;
 
@@ -227,6 +228,27 @@ typedef struct hmrt_window_sections {
  * the colour map likewise at the finest resolution.  d_window_color_map may be NULL.  Asynchronous on the context's stream. */
 int hmrt_compose_window(hmrt_ctx* ctx, const hmrt_window_sections* sections, int coarse_res, int levels, int cell_x, int cell_y,
                         float* d_window_pyramid, hmrt_color* d_window_color_map);
+
+/* ---- multi-GPU exchange steps --------------------------------------------------------- */
+
+/*
+ * For C / C++ hosts that run one context per GPU (one process per GPU, or one process driving several): the two collective
+ * steps of the path, on the CALLER'S NCCL communicator (`nccl_comm` is this rank's ncclComm_t passed as void*).  The
+ * library has no link-time NCCL dependency: libnccl.so.2 is looked up with dlopen on first use (the copy already loaded in
+ * the process, if any), HMRT_E_NCCL if there is none.  Both calls are asynchronous on the context's stream; a process
+ * that drives several ranks from one thread wraps the per-rank calls in ncclGroupStart / ncclGroupEnd as usual.
+ * (Python hosts use torch.distributed for the same two steps, hmrt/dist.py.)
+ *
+ * hmrt_broadcast_heightmap: replicate the pyramid (and colour map, if given) of rank `root` -- the heightmap is replicated,
+ * the image is sharded by row tiles (hmrt_trace_opts.tile_first / tile_stride).
+ * hmrt_allreduce_max_heights: combine per-rank partial rasterisations: MAX over the finest level viewed as int32 (heights
+ * are >= +0, so integer order == float order, NaN-free and exact) and, if given, over the colour keys as int64 (the last
+ * writer in file order wins on every rank); follow with hmrt_build_mips / hmrt_resolve_colors on every rank.
+ */
+int hmrt_broadcast_heightmap(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid, hmrt_color* d_color_map, int coarse_res,
+                             int levels, int root);
+int hmrt_allreduce_max_heights(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid, uint64_t* d_color_keys, int coarse_res,
+                               int levels);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 
