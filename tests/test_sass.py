@@ -38,7 +38,8 @@ def sass():
 def test_every_kernel_is_present(sass):
     names = " ".join(sass)
     for k in ["trace_persistent_kernel", "top_level_max_kernel", "scatter_las_kernel", "scatter_xyz_kernel", "bin_points_kernel",
-              "apply_bins_kernel", "build_mips_fused_kernel", "build_mip_level_kernel", "resolve_colors_kernel", "locality_probe_kernel"]:
+              "apply_bins_kernel", "build_mips_fused_kernel", "build_mip_level_kernel", "resolve_colors_kernel", "locality_probe_kernel",
+              "compose_window_kernel", "compose_colors_kernel"]:
         assert k in names, f"{k} missing from libhmrt.so"
 
 
