@@ -41,6 +41,9 @@ POSES = 16
 FRAME_DIM = (32.0, 18.0, 20.0)  # main.cpp:57
 NCU_DRAM_BYTES_PER_LAUNCH = 2.225832e9 + 0.377172e9  # profiles/ncu_trace_r01_e.txt (1 GPU, 16 frames per launch): dram__bytes_read.sum + dram__bytes_write.sum
 NCU_SOURCE = "profiles/ncu_trace_r01_e.txt"
+# the same capture: what actually limits the kernel (it is pipe/issue-bound, DRAM is 4 % busy)
+NCU_PIPES = {"issue_slots_busy_pct": 72.1, "fma_pipe_cycles_active_pct": 61.1, "alu_pipe_pct": 38.3, "dram_throughput_pct": 4.0,
+             "active_lanes_per_instruction": 27.6, "warp_instructions_per_launch": 6.572e9}
 WORKLOAD = f"{R0}^2 heightmap ({LEVELS}-level max-mip pyramid, 1.43 GB), {W}x{H} primary rays + height-ramp shading, {POSES} camera poses per step"
 
 
@@ -351,7 +354,7 @@ def _run_gpu_arm(args):
     traffic = NCU_DRAM_BYTES_PER_LAUNCH / world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": NCU_SOURCE, "kernel": "trace_persistent_kernel<false, kWalkFastPow2>", "peak_source": peak_src,
-                "iterations_per_ray": iters / (rays_per_step * args.steps),
+                "iterations_per_ray": iters / (rays_per_step * args.steps), "ncu_pipes": NCU_PIPES,
                 "algorithmic_bytes_per_launch": algo_bytes / max(1, args.steps) / world,
                 "note": "issue-bound, not bandwidth-bound: algorithmic bytes are the reference algorithm's height fetches (4 B x loop iterations + 3 B RGB per ray); "
                         "most of them hit L1/L2, so DRAM traffic is ~13x smaller (see DESIGN.md section 4.1)"}
