@@ -130,6 +130,24 @@ def test_trace_host_matches_device_and_reference_call_order(cuda_ctx):
     assert e.value.code == -2
 
 
+@pytest.mark.parametrize("W,H,n_frames,stride", [(3840, 2160, 1, 1), (3840, 2157, 3, 1), (3840, 2160, 5, 2), (2560, 1083, 2, 1)])
+def test_trace_host_large_frames_split_last_launch(cuda_ctx, W, H, n_frames, stride):
+    """hmrt_trace_host groups frames into launches of >= 4 M rays and cuts the LAST single-frame launch into four tile ranges
+    with their own device->host copies; the host buffer must equal the device rendering of hmrt_trace byte for byte --
+    whole frames, ragged last row tile (H % 8 != 0), row-tile sharding."""
+    import gpulib
+
+    sc = ol.scene("r1024_l8", seed=3)
+    keep = gpulib.upload_scene(cuda_ctx, sc)  # noqa: F841
+    cams = ol.cameras_for(sc, n_frames)
+    for first in range(stride):
+        opts = ol.make_opts(sc["max_height"], shadows=True, tile_first=first, tile_stride=stride)
+        dev, _ = gpulib.gpu_trace(cuda_ctx, W, H, cams, opts, hits=False)
+        host = torch.full(dev.shape, 77, dtype=torch.uint8).pin_memory()
+        cuda_ctx.trace_host(W, H, cams, opts, host)
+        assert (host.numpy() == dev).all()
+
+
 def test_error_codes(cuda_ctx):
     import gpulib
     import hmrt
