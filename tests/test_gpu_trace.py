@@ -148,6 +148,29 @@ def test_trace_host_large_frames_split_last_launch(cuda_ctx, W, H, n_frames, str
         assert (host.numpy() == dev).all()
 
 
+def test_many_frames_in_one_call_equal_single_frame_calls(cuda_ctx):
+    """More frames than fit in the kernel parameters (48) travel through the device-side frame table; device and host
+    output of a 70-frame call must equal 70 single-frame calls."""
+    import gpulib
+
+    sc = ol.scene("r512_l4", seed=6)
+    keep = gpulib.upload_scene(cuda_ctx, sc)  # noqa: F841
+    W, H, n = 96, 64, 70
+    base = ol.cameras_for(sc, 6)
+    cams = []
+    for i in range(n):  # 70 distinct cameras: the scene cameras, shifted
+        c = base[i % len(base)]
+        cams.append(ol.make_camera((c.position[0] + 1.5 * (i // 7), c.position[1] + 0.25 * i, c.position[2] - 0.75 * (i // 7)), tuple(c.forward)))
+    opts = ol.make_opts(sc["max_height"], shadows=True)
+    many, _ = gpulib.gpu_trace(cuda_ctx, W, H, cams, opts, hits=False)
+    for i in (0, 1, 47, 48, 49, 69):
+        one, _ = gpulib.gpu_trace(cuda_ctx, W, H, [cams[i]], opts, hits=False)
+        assert (many[i] == one[0]).all(), i
+    host = torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory()
+    cuda_ctx.trace_host(W, H, cams, opts, host)
+    assert (host.numpy() == many).all()
+
+
 def test_error_codes(cuda_ctx):
     import gpulib
     import hmrt
