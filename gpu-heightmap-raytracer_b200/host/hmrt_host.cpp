@@ -415,12 +415,31 @@ static Vec3 normalize(Vec3 v) {
   return {v.x * s, v.y * s, v.z * s};
 }
 static Vec3 cross(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
-/* glm::rotate(v, angle, axis) (gtx/rotate_vector): Rodrigues' formula */
-static Vec3 rotate(Vec3 v, float angle, Vec3 k) {
+/* glm::rotate(v, angle, axis) as GLM 0.9.8.3 evaluates it (inc/glm/gtx/rotate_vector.inl:45-53): the upper 3x3 of
+ * rotate(mat4(1), angle, axis) (gtc/matrix_transform.inl:19-47) times v (detail/type_mat3x3.inl:430-433), in that
+ * operation order, so that a fly-through replays bit for bit (tests/test_refhost.py). */
+static Vec3 rotate(Vec3 v, float angle, Vec3 normal) {
   const float c = std::cos(angle), s = std::sin(angle);
-  const Vec3 kxv = cross(k, v);
-  const float kv = (k.x * v.x + k.y * v.y + k.z * v.z) * (1 - c);
-  return {v.x * c + kxv.x * s + k.x * kv, v.y * c + kxv.y * s + k.y * kv, v.z * c + kxv.z * s + k.z * kv};
+  const Vec3 axis = normalize(normal);
+  const Vec3 temp = {(1.0f - c) * axis.x, (1.0f - c) * axis.y, (1.0f - c) * axis.z};
+  float R[3][3]; /* Rotate[column][row] */
+  R[0][0] = c + temp.x * axis.x;
+  R[0][1] = temp.x * axis.y + s * axis.z;
+  R[0][2] = temp.x * axis.z - s * axis.y;
+  R[1][0] = temp.y * axis.x - s * axis.z;
+  R[1][1] = c + temp.y * axis.y;
+  R[1][2] = temp.y * axis.z + s * axis.x;
+  R[2][0] = temp.z * axis.x + s * axis.y;
+  R[2][1] = temp.z * axis.y - s * axis.x;
+  R[2][2] = c + temp.z * axis.z;
+  float M[3][3]; /* Result[k] = m[0] * R[k][0] + m[1] * R[k][1] + m[2] * R[k][2] with m = identity */
+  for (int k = 0; k < 3; ++k) {
+    M[k][0] = 1.0f * R[k][0] + 0.0f * R[k][1] + 0.0f * R[k][2];
+    M[k][1] = 0.0f * R[k][0] + 1.0f * R[k][1] + 0.0f * R[k][2];
+    M[k][2] = 0.0f * R[k][0] + 0.0f * R[k][1] + 1.0f * R[k][2];
+  }
+  return {M[0][0] * v.x + M[1][0] * v.y + M[2][0] * v.z, M[0][1] * v.x + M[1][1] * v.y + M[2][1] * v.z,
+          M[0][2] * v.x + M[1][2] * v.y + M[2][2] * v.z};
 }
 
 void Camera::move(float fwd, float right, float up, float dt, const float boundaries[2], float max_height) {

@@ -45,6 +45,27 @@ build_variant() {  # $1 = output name, $2... = extra defines
 build_variant libhmrt_ref -DHMRT_REF_FLOAT_MATH   # canonical: pow(float,int) in fp32 (MSVC/CUDA 8)
 build_variant libhmrt_ref_dpow                   # variant: g++/nvcc-Linux promotion to double
 
+# The reference's own HOST-side hot-path code (rasteriser loop, section walk, window composition, camera), cut verbatim out
+# of main.cpp by line range and compiled against stub liblas / thread / ifstream types: see refhost_harness.cpp.
+build_refhost() {  # $1 = output name, $2 = main.cpp to cut from
+  sed -n '44,618p;745,781p' "$2" > "$tmp/$1_cut_main.inc"
+  sed -n '995,1003p' "$2" > "$tmp/$1_cut_tables.inc"
+  # -fno-aggressive-loop-optimizations: preparePointBuffer's index searches (main.cpp:474,482,490,498) test
+  # `origins[maxX][0].x` BEFORE `maxX < point_sections_size`, i.e. they read one element past the inner array on their
+  # last trip.  MSVC compiles that as written (a harmless read of the neighbouring row); g++ -O2 treats the out-of-bounds
+  # read as proof that the index test can never fail and drops it, and the window then comes from the wrong sections.
+  g++ "${cxxflags[@]}" -fno-aggressive-loop-optimizations -DHMRT_REF_FLOAT_MATH -D__device__= -D__global__= -D__host__= \
+      -DREFHOST_CUT_MAIN="\"$tmp/$1_cut_main.inc\"" -DREFHOST_CUT_TABLES="\"$tmp/$1_cut_tables.inc\"" \
+      -shared -o "$out/$1.so" "$here/refhost_harness.cpp" -lpthread
+}
+build_refhost libhmrt_refhost "$ref/src/main.cpp"      # verbatim: 4x4 sections, 8 levels (main.cpp:74,83)
+# variant with ONLY the two compile-time constants changed (3x3 sections, 4 levels), for small fast cases
+sed -e 's/^const int point_sections_size = 4;/const int point_sections_size = 3;/' \
+    -e 's/^const int LOD_levels = 8;/const int LOD_levels = 4;/' "$ref/src/main.cpp" > "$tmp/main_g3l4.cpp"
+[ "$(diff "$ref/src/main.cpp" "$tmp/main_g3l4.cpp" | grep -c '^>')" = 2 ] || { echo "build_ref.sh: constant patch did not apply" >&2; exit 1; }
+build_refhost libhmrt_refhost_g3l4 "$tmp/main_g3l4.cpp"
+echo "built $out/libhmrt_refhost.so $out/libhmrt_refhost_g3l4.so (reference main.cpp:44-618,745-781,995-1003 for the host)"
+
 # The reference's CUDA kernel itself, recompiled for sm_100a (baseline "reference kernel on B200").
 if command -v nvcc >/dev/null 2>&1; then
   cp "$ref/src/CudaKernel.cu" "$tmp/CudaKernel_ref.cu"   # temp copy so that its #include "CudaKernel.cuh" finds the patched header
