@@ -7,14 +7,23 @@ height-ramp shading, POSES camera poses per step.  A "step" is one pass of the t
 batch of POSES frames; every step uses a different pose batch, and the pyramid is far larger
 than L2, so successive steps do not replay a cached working set.
 
+Both arms build the terrain with the SAME host code (torch CPU ops, fixed seed): identical bytes, checked by a
+checksum both arms print.  The GPU arm uploads it and builds the mip levels with the product's kernel.
+
 N > 1 (torchrun, one rank per GPU): rank 0 builds the pyramid and broadcasts it over NCCL/NVLink;
 each frame is cut into 8-row tiles interleaved across ranks (no collective on the per-frame data
 path).  Total work per step is fixed -> "scaling": "strong".
 
+Timing: W warm-up steps, then the K steps are timed; when K steps last less than --min-seconds (1 s) the K-step loop
+is repeated R times inside ONE timed region (same K pose batches) and ms_per_step = region / (K * R), so that the
+region is long enough for clock sampling at every N.  Consecutive steps are independent frames batches: they are
+issued alternately on two CUDA streams with their own framebuffers (a double-buffered renderer), so the drain of
+one step's persistent kernel runs under the head of the next.
+
 `--impl reference` times the reference's own CPU code (oracle/_ref: CudaKernel.cu host-compiled;
 the oracle port if that library is absent) on the host cores over a bounded row sample of the
 same workload.  Nothing under oracle/ is used by the measured GPU arm except as the separately
-reported `cpu_baseline`.
+reported `cpu_baseline` (whose rows double as the `parity` check of the GPU frames).
 """
 from __future__ import annotations
 
@@ -39,66 +48,77 @@ COARSE = R0 >> (LEVELS - 1)
 W, H = 3840, 2160
 POSES = 16
 FRAME_DIM = (32.0, 18.0, 20.0)  # main.cpp:57
-NCU_DRAM_BYTES_PER_LAUNCH = 2.225832e9 + 0.377172e9  # profiles/ncu_trace_r01_e.txt (1 GPU, 16 frames per launch): dram__bytes_read.sum + dram__bytes_write.sum
-NCU_SOURCE = "profiles/ncu_trace_r01_e.txt"
-# the same capture: what actually limits the kernel (it is pipe/issue-bound, DRAM is 4 % busy)
-NCU_PIPES = {"issue_slots_busy_pct": 72.1, "fma_pipe_cycles_active_pct": 61.1, "alu_pipe_pct": 38.3, "dram_throughput_pct": 4.0,
-             "active_lanes_per_instruction": 27.6, "warp_instructions_per_launch": 6.572e9}
 WORKLOAD = f"{R0}^2 heightmap ({LEVELS}-level max-mip pyramid, 1.43 GB), {W}x{H} primary rays + height-ramp shading, {POSES} camera poses per step"
+# the SAME dict in both arms (the driver compares them)
+CONFIG = {
+    "workload": WORKLOAD,
+    "l2": "inputs larger than L2 (1.43 GB pyramid); a different pose batch every step",
+    "levels": LEVELS,
+    "frame_dimension": list(FRAME_DIM),
+    "poses_per_step": POSES,
+    "pose_family": "altitude 2000-4000 cells above the terrain maximum, pitch -0.10..-0.35, all headings, positions spread over the map",
+    "terrain": "analytic hills + seeded noise generated on the HOST by the same code in both arms (identical bytes; see terrain_checksum)",
+}
+NCU_SUMMARY = REPO / "profiles" / "ncu_trace_r02.json"  # per-launch counters of the dominant kernel from the committed ncu capture
+RASTER_POINTS = 500_000_000  # BASELINE.json configs[3]
 
 
 # ------------------------------------------------------------------------------------------------
 # workload definition (shared by both arms; pure host logic)
 
-def pose_batch(step: int, max_height: float):
-    """POSES deterministic camera poses for step `step`: altitude 2000-4000 cells, pitch -0.35..-0.1,
-    headings all around, positions spread over the map."""
+def pose_batch(step: int, max_height: float, family: str = "high"):
+    """POSES deterministic camera poses for step `step`.
+    "high" (the metric's family): altitude 2000-4000 cells, pitch -0.35..-0.1.
+    "low"  (descent-dominated views): altitude 200-500 cells above the terrain maximum, pitch -0.3..-3 (down to nadir-like)."""
     poses = []
     for i in range(POSES):
         k = step * POSES + i
         u = (k * 0.6180339887498949) % 1.0
         v = (k * 0.7548776662466927) % 1.0
         heading = 2 * math.pi * ((k * 0.5698402909980532) % 1.0)
-        pitch = -0.10 - 0.25 * ((k * 0.3819660112501051) % 1.0)
-        alt = max_height + 2000.0 + 2000.0 * ((k * 0.2451223337533073) % 1.0)
+        a = (k * 0.3819660112501051) % 1.0
+        b = (k * 0.2451223337533073) % 1.0
+        if family == "high":
+            pitch = -0.10 - 0.25 * a
+            alt = max_height + 2000.0 + 2000.0 * b
+        else:
+            pitch = -0.3 * (10.0 ** a)  # -0.3 .. -3.0: from a shallow look down to ~72 degrees below the horizon
+            alt = max_height + 200.0 + 300.0 * b
         pos = (R0 * (0.2 + 0.6 * u), alt, R0 * (0.2 + 0.6 * v))
         fwd = (math.cos(heading), pitch, math.sin(heading))
         poses.append((pos, fwd))
     return poses
 
 
-def make_cameras(hmrt, step, max_height):
-    return [hmrt.camera(p, f, FRAME_DIM) for p, f in pose_batch(step, max_height)]
+def make_cameras(hmrt, step, max_height, family="high"):
+    return [hmrt.camera(p, f, FRAME_DIM) for p, f in pose_batch(step, max_height, family)]
 
 
-def build_terrain(torch, ctx, hmrt):
-    """Synthetic terrain on the device (torch used as a buffer filler), then the product's own mip kernel."""
-    res, idx, total = hmrt.pyramid_layout(COARSE, LEVELS)
-    pyr = torch.zeros(total, dtype=torch.float32, device="cuda")
-    fin = pyr[idx[0]:].view(R0, R0)
-    xs = torch.arange(R0, device="cuda", dtype=torch.float32)
-    x, z = xs[None, :], xs[:, None]
-    fin.copy_(420 + 260 * torch.sin(x * 0.00121) * torch.cos(z * 0.00097) + 110 * torch.sin(x * 0.0047 + z * 0.0039)
-              + 45 * torch.sin(x * 0.019) * torch.sin(z * 0.023) + 12 * torch.sin(x * 0.11 + z * 0.07))
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    fin.add_(torch.rand((R0, R0), device="cuda", generator=g) * 3.0).clamp_(min=0)
-    ctx.build_mips(pyr, COARSE, LEVELS)
-    torch.cuda.synchronize()
-    return pyr, float(fin.max())
-
-
-def terrain_cpu_rows(n_threads_hint=None):
-    """Same terrain on the host for the CPU arm (numpy; only the reference/oracle arm uses it)."""
+def build_terrain_host() -> np.ndarray:
+    """The finest level [R0, R0] float32 on the HOST -- the one terrain generator of both arms (same torch CPU code, same
+    seed, same box => same bytes).  ~5 s."""
     import torch  # CPU tensors only
 
     xs = torch.arange(R0, dtype=torch.float32)
     x, z = xs[None, :], xs[:, None]
-    fin = (420 + 260 * torch.sin(x * 0.00121) * torch.cos(z * 0.00097) + 110 * torch.sin(x * 0.0047 + z * 0.0039)
-           + 45 * torch.sin(x * 0.019) * torch.sin(z * 0.023) + 12 * torch.sin(x * 0.11 + z * 0.07))
-    # the CPU arm times the traversal; it does not need the GPU arm's exact noise bits
+    fin = torch.empty((R0, R0), dtype=torch.float32)
+    torch.mul((torch.sin(xs * 0.00121) * 260)[None, :], torch.cos(xs * 0.00097)[:, None], out=fin)
+    fin += 420
+    tmp = x * 0.0047 + z * 0.0039
+    fin += tmp.sin_().mul_(110)
+    fin += (torch.sin(xs * 0.019) * 45)[None, :] * torch.sin(xs * 0.023)[:, None]
+    torch.add(x * 0.11, z * 0.07, out=tmp)
+    fin += tmp.sin_().mul_(12)
     g = torch.Generator().manual_seed(1234)
-    fin.add_(torch.rand((R0, R0), generator=g) * 3.0).clamp_(min=0)
+    tmp.uniform_(0.0, 3.0, generator=g)
+    fin += tmp
+    fin.clamp_(min=0)
     return fin.numpy()
+
+
+def terrain_checksum(fin: np.ndarray) -> str:
+    w = np.ascontiguousarray(fin).view(np.uint32).ravel()
+    return f"{int(w.sum(dtype=np.uint64)):016x}-{int(np.bitwise_xor.reduce(w)):08x}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -168,11 +188,14 @@ def _load_cpu_impl():
     return "port", ol.oracle().hmrt_oracle_trace, ol
 
 
-def cpu_sample_rate(pyramid_host: np.ndarray, max_height: float, step: int, budget_s: float, n_threads: int):
-    """Trace 8-row bands, spread over the frames of pose batch `step`, until `budget_s` is spent.
-    Returns (Mrays/s, rays traced, seconds, kind)."""
+def cpu_sample_rate(pyramid_host: np.ndarray, max_height: float, step: int, budget_s: float, n_threads: int, family="high",
+                    compare_with=None):
+    """Trace 8-row bands, spread over the frames of pose batch `step`, until `budget_s` of tracing time is spent.
+    `compare_with` (optional, [POSES, H, W, 3] uint8 host array of the GPU's frames of the same pose batch): every traced
+    band is compared with the same rows of it (outside the timed part).
+    Returns (Mrays/s, rays traced, seconds, kind, parity dict or None)."""
     kind, fn, ol = _load_cpu_impl()
-    cams = [ol.make_camera(p, f, FRAME_DIM) for p, f in pose_batch(step, max_height)]
+    cams = [ol.make_camera(p, f, FRAME_DIM) for p, f in pose_batch(step, max_height, family)]
     opts = ol.make_opts(max_height)
     rgb = np.zeros((H, W, 3), np.uint8)
     rows_per_call = max(8, 2 * n_threads)
@@ -181,19 +204,29 @@ def cpu_sample_rate(pyramid_host: np.ndarray, max_height: float, step: int, budg
     bands = [(b * (H // 8) + off + shift) for shift in range(0, rows_per_call, 8) for off in range(0, H // 8, rows_per_call)
              for b in range(8)]
     bands = bands * len(cams)
-    rays, t0 = 0, time.perf_counter()
+    rays, spent = 0, 0.0
+    par = {"rows": 0, "pixels": 0, "pixels_differ": 0, "frames_touched": 0, "checked_against": f"oracle/_ref ({kind})"} if compare_with is not None else None
+    touched = set()
     for j, r0 in enumerate(bands):
-        cam = cams[(j // 8) % len(cams)]
+        ci = (j // 8) % len(cams)
         r1 = min(H, r0 + rows_per_call)
-        rc = fn(pyramid_host.ctypes.data, None, COARSE, LEVELS, W, H, C.byref(cam), C.byref(opts), n_threads, r0, r1,
+        t0 = time.perf_counter()
+        rc = fn(pyramid_host.ctypes.data, None, COARSE, LEVELS, W, H, C.byref(cams[ci]), C.byref(opts), n_threads, r0, r1,
                 rgb.ctypes.data, None)
+        spent += time.perf_counter() - t0
         if rc != 0:
             raise RuntimeError(f"cpu arm failed: {rc}")
         rays += (r1 - r0) * W
-        if time.perf_counter() - t0 >= budget_s:
+        if par is not None:
+            par["rows"] += r1 - r0
+            par["pixels"] += (r1 - r0) * W
+            par["pixels_differ"] += int((rgb[r0:r1] != compare_with[ci, r0:r1]).any(axis=2).sum())
+            touched.add(ci)
+        if spent >= budget_s:
             break
-    dt = time.perf_counter() - t0
-    return rays / dt / 1e6, rays, dt, kind
+    if par is not None:
+        par["frames_touched"] = len(touched)
+    return rays / spent / 1e6, rays, spent, kind, par
 
 
 def host_pyramid_from_finest(fin: np.ndarray) -> np.ndarray:
@@ -208,7 +241,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     n_threads = os.cpu_count() or 1
-    fin = terrain_cpu_rows()
+    fin = build_terrain_host()
+    checksum = terrain_checksum(fin)
     pyr = host_pyramid_from_finest(fin)
     mh = float(fin.max())
     per_step_budget = max(0.5, min(4.0, 150.0 / max(1, args.steps)))  # the whole arm stays within a few minutes for any --steps
@@ -216,7 +250,7 @@ def run_reference_arm(args):
         cpu_sample_rate(pyr, mh, s, min(1.0, per_step_budget), n_threads)
     rays_total, t_total, kind = 0, 0.0, "port"
     for s in range(args.steps):
-        _, rays, dt, kind = cpu_sample_rate(pyr, mh, args.warmup + s, per_step_budget, n_threads)
+        _, rays, dt, kind, _ = cpu_sample_rate(pyr, mh, args.warmup + s, per_step_budget, n_threads)
         rays_total += rays
         t_total += dt
     value = rays_total / t_total / 1e6
@@ -224,8 +258,8 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (1.43 GB pyramid)", "arm": "reference CPU code on host cores"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "terrain_checksum": checksum,
+        "arm": "the reference's own CPU code (oracle/_ref) on all host cores",
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": n_threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -254,6 +288,109 @@ def run_gpu_arm(args):
     return 0
 
 
+class StepRunner:
+    """Issues trace steps alternately on two streams with their own framebuffers and times whole regions on the device."""
+
+    def __init__(self, torch, dist, ctx, world, fbs):
+        self.torch, self.dist, self.ctx, self.world, self.fbs = torch, dist, ctx, world, fbs
+        self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self.issued = 0
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def issue(self, cams, opts, hits=None):
+        k = self.issued & 1
+        self.issued += 1
+        with self.torch.cuda.stream(self.streams[k]):
+            self.ctx.trace(W, H, cams, opts, out=self.fbs[k], hits=hits if hits is not None else False)
+
+    def timed(self, cam_batches, opts, repeats=1):
+        """Device time (ms) of len(cam_batches) * repeats steps, max over ranks, bracketed by barrier + synchronize."""
+        torch = self.torch
+        self.barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        t_begin = time.time()
+        start.record(cur)
+        for s in self.streams:
+            s.wait_event(start)
+        for _ in range(repeats):
+            for cams in cam_batches:
+                self.issue(cams, opts)
+        for s in self.streams:
+            cur.wait_stream(s)
+        stop.record(cur)
+        self.barrier()
+        t_end = time.time()
+        ms = start.elapsed_time(stop)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t_begin, t_end
+
+    def pick_repeats(self, cam_batches, opts, min_seconds):
+        ms, _, _ = self.timed(cam_batches, opts, 1)
+        return max(1, int(math.ceil(min_seconds * 1e3 / max(ms, 1e-3))))
+
+
+def _allsum(torch, dist, world, v):
+    if world == 1:
+        return int(v)
+    t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def _frames_hash(torch, fb, tile_first, tile_stride):
+    """Order-independent 63-bit hash contribution of this rank's rows of one step's frames: sum over bytes of
+    byte * odd weight(global position).  Summed over ranks it is the same number for every N iff the frames are."""
+    from hmrt import HMRT_ROW_TILE
+
+    n, rows, w, _ = fb.shape
+    tiles = torch.arange(tile_first, tile_first + (rows + HMRT_ROW_TILE - 1) // HMRT_ROW_TILE * tile_stride, tile_stride, device=fb.device)
+    grow = (tiles[:, None] * HMRT_ROW_TILE + torch.arange(HMRT_ROW_TILE, device=fb.device)[None, :]).reshape(-1)[:rows]  # global row of each local row
+    total = torch.zeros((), dtype=torch.int64, device=fb.device)
+    col = torch.arange(w * 3, device=fb.device, dtype=torch.int64)
+    for f in range(n):
+        pos = (f * H + grow.to(torch.int64))[:, None] * (w * 3) + col[None, :]
+        total += (fb[f].reshape(rows, w * 3).to(torch.int64) * (pos * 2654435761 % 2147483647 * 2 + 1)).sum()
+    return int(total.item()) & ((1 << 63) - 1)
+
+
+def _tolerance_agreement(torch, hits_exact, rgb_exact, hits_tol, rgb_tol, cam_positions):
+    """North-star acceptance bars of the tolerance mode against the exact walk (== the reference, see `parity`) on the same
+    frames: hit cell, hit distance from the camera (on pixels that hit the same cell), colour."""
+    fe, ft = hits_exact[..., 3], hits_tol[..., 3]
+    hit_e, hit_t = (fe & 1) != 0, (ft & 1) != 0
+    pe = hits_exact[..., :3].view(torch.float32)
+    pt = hits_tol[..., :3].view(torch.float32)
+    both = hit_e & hit_t
+    same_cell = (torch.floor(pe[..., 0]) == torch.floor(pt[..., 0])) & (torch.floor(pe[..., 2]) == torch.floor(pt[..., 2])) & ((fe & 6) == (ft & 6))
+    cell_ok = (both & same_cell) | (~hit_e & ~hit_t)
+    n = hit_e.numel()
+
+    def dist_to_camera(p, flags):
+        x = torch.where((flags & 2) != 0, float(R0) - p[..., 0], p[..., 0]).double()
+        z = torch.where((flags & 4) != 0, float(R0) - p[..., 2], p[..., 2]).double()
+        c = cam_positions.double()[:, None, None, :]
+        return torch.sqrt((x - c[..., 0]) ** 2 + (p[..., 1].double() - c[..., 1]) ** 2 + (z - c[..., 2]) ** 2)
+
+    de, dt = dist_to_camera(pe, fe), dist_to_camera(pt, ft)
+    ok = both & same_cell
+    rel = torch.where(ok, (de - dt).abs() / de.clamp(min=1e-9), torch.zeros_like(de))
+    col = (rgb_exact.to(torch.int16) - rgb_tol.to(torch.int16)).abs().amax(dim=-1)
+    return {"pixels": n, "hit_cell_match_pct": 100.0 * int(cell_ok.sum().item()) / n,
+            "hit_miss_flips": int((hit_e != hit_t).sum().item()),
+            "max_relative_hit_distance_error_on_matching_cells": float(rel.max().item()),
+            "colour_within_1_of_255_pct": 100.0 * int((col <= 1).sum().item()) / n,
+            "pixel_exact_pct": 100.0 * int((col == 0).sum().item()) / n,
+            "bars": "north star: hit cell >= 99.9 %, hit distance within 1e-4 relative, colour within 1/255, >= 95 % pixel-exact"}
+
+
 def _run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -274,12 +411,20 @@ def _run_gpu_arm(args):
 
     sampler = ClockSampler(local) if rank == 0 else None  # started early (nvidia-smi is slow to start); filtered to the timed window
     ctx = hmrt.Context(local)
-    # heightmap: built on rank 0 with the product's kernels, replicated by one broadcast over NVLink
+    # heightmap: generated on rank 0's host (same code as the reference arm), mip levels by the product's kernel, replicated
+    # by one broadcast over NVLink
     res, idx, total = hmrt.pyramid_layout(COARSE, LEVELS)
+    pyr = torch.empty(total, dtype=torch.float32, device="cuda")
+    mh, checksum, fin_host = 0.0, None, None
     if rank == 0:
-        pyr, mh = build_terrain(torch, ctx, hmrt)
-    else:
-        pyr, mh = torch.empty(total, dtype=torch.float32, device="cuda"), 0.0
+        fin_host = build_terrain_host()
+        checksum = terrain_checksum(fin_host)
+        mh = float(fin_host.max())
+        pyr[idx[0]:].view(R0, R0).copy_(torch.from_numpy(fin_host))
+        ctx.build_mips(pyr, COARSE, LEVELS)
+        torch.cuda.synchronize()
+        if world > 1 or args.no_cpu_baseline:
+            fin_host = None
     bcast_ms = None
     if world > 1:
         mh_t = torch.tensor([mh], dtype=torch.float32, device="cuda")
@@ -298,93 +443,172 @@ def _run_gpu_arm(args):
     tile_first, tile_stride = hd.tiles_for_rank(rank, world)
     opts = hmrt.trace_opts(mh, tile_first=tile_first, tile_stride=tile_stride)
     rows = hmrt.rows_local(H, tile_first, tile_stride)
-    fb = torch.empty((POSES, rows, W, 3), dtype=torch.uint8, device="cuda")
-    cams_by_step = [hmrt.context._cam_array(make_cameras(hmrt, s, mh)) for s in range(args.warmup + args.steps)]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    fbs = [torch.empty((POSES, rows, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    K, Wu = args.steps, args.warmup
+    cams_by_step = [hmrt.context._cam_array(make_cameras(hmrt, s, mh)) for s in range(Wu + K)]
+    timed_batches = cams_by_step[Wu:]
+    run = StepRunner(torch, dist, ctx, world, fbs)
+    rays_per_step = POSES * W * H
 
     # ---- value: inputs resident, device-timed --------------------------------------------------
-    for s in range(args.warmup):
-        ctx.trace(W, H, cams_by_step[s], opts, out=fb)
-    barrier()
-    t_begin = time.time()
-    launches0 = ctx.launch_count
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for s in range(args.steps):
-        ctx.trace(W, H, cams_by_step[args.warmup + s], opts, out=fb)
-    stop.record()
-    barrier()
-    launches = ctx.launch_count - launches0
-    ms = start.elapsed_time(stop)
-    t_end = time.time()
-    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    for s in range(Wu):
+        run.issue(cams_by_step[s], opts)
+    repeats = run.pick_repeats(timed_batches, opts, args.min_seconds)
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    rays_per_step = POSES * W * H
-    value = rays_per_step * args.steps / (ms * 1e-3) / 1e6
+        r_t = torch.tensor([repeats], dtype=torch.int64, device="cuda")
+        dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+        repeats = int(r_t.item())
+    launches0 = ctx.launch_count
+    ms, t_begin, t_end = run.timed(timed_batches, opts, repeats)
+    launches = _allsum(torch, dist, world, ctx.launch_count - launches0)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    steps_timed = K * repeats
+    value = rays_per_step * steps_timed / (ms * 1e-3) / 1e6
 
     # ---- algorithmic bytes of the timed steps: 4 B per traversal iteration + 3 B RGB per ray ----
-    iters = 0
     hit_buf = torch.empty((POSES, rows, W, 4), dtype=torch.int32, device="cuda")
-    for s in range(args.steps):
-        ctx.trace(W, H, cams_by_step[args.warmup + s], opts, out=fb, hits=hit_buf)
-        iters += int((hit_buf[..., 3].view(torch.int32) >> 8).to(torch.int64).sum().item())
-    del hit_buf
-    if world > 1:
-        it = torch.tensor([iters], dtype=torch.int64, device="cuda")
-        dist.all_reduce(it, op=dist.ReduceOp.SUM)
-        iters = int(it.item())
-    algo_bytes = 4 * iters + 3 * rays_per_step * args.steps
+    ctx.trace_stats(reset=True)
+    frames_hash = 0
+    for i, cams in enumerate(timed_batches):
+        ctx.trace(W, H, cams, opts, out=fbs[0], hits=hit_buf)
+        if i == 0:
+            frames_hash = _frames_hash(torch, fbs[0], tile_first, max(1, tile_stride))
+    st = ctx.trace_stats(reset=True)
+    iters = _allsum(torch, dist, world, st["iterations"])
+    air_iters = _allsum(torch, dist, world, st["air_iterations"])
+    frames_hash = _allsum(torch, dist, world, frames_hash) & ((1 << 63) - 1)
+    algo_bytes_k = 4 * iters + 3 * rays_per_step * K  # of the K distinct steps
     peaks_path = REPO / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = algo_bytes / (ms * 1e-3) / 1e9 / world  # per GPU, like the per-GPU peak
-    # DRAM traffic of one single-GPU launch (16 frames) from the committed ncu capture: dram__bytes_read.sum + dram__bytes_write.sum
-    traffic = NCU_DRAM_BYTES_PER_LAUNCH / world
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": NCU_SOURCE, "kernel": "trace_persistent_kernel<false, kWalkFastPow2>", "peak_source": peak_src,
-                "iterations_per_ray": iters / (rays_per_step * args.steps), "ncu_pipes": NCU_PIPES,
-                "algorithmic_bytes_per_launch": algo_bytes / max(1, args.steps) / world,
-                "note": "issue-bound, not bandwidth-bound: algorithmic bytes are the reference algorithm's height fetches (4 B x loop iterations + 3 B RGB per ray); "
-                        "most of them hit L1/L2, so DRAM traffic is ~13x smaller (see DESIGN.md section 4.1)"}
+    achieved = algo_bytes_k * repeats / (ms * 1e-3) / 1e9 / world  # per GPU, like the per-GPU peak
+    fetched_bytes_k = 4 * (iters - air_iters) + 3 * rays_per_step * K  # air-phase iterations issue no load at all
+    ncu = json.loads(NCU_SUMMARY.read_text()) if NCU_SUMMARY.exists() else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue = None
+    if ncu:
+        # warp instructions per loop iteration of the captured launch x the iterations of the timed steps: the share of the
+        # issue slots (148 SMs x 4 sub-partitions x f_SM) the kernel used
+        inst = ncu["warp_instructions_per_launch"] / ncu["iterations_per_launch"] * iters * repeats / world
+        issue = {"warp_instructions_est": inst, "issue_slot_frac": inst / (ms * 1e-3) / (148 * 4 * sm_mhz * 1e6),
+                 "how": f"warp instructions per iteration from {ncu['source']} x iterations of the timed steps / (time x 148 SMs x 4 SMSPs x {sm_mhz:.0f} MHz)",
+                 "ncu_pipes": ncu.get("pipes")}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (ncu["dram_bytes_per_launch"] / world) if ncu else None, "traffic_source": ncu["source"] if ncu else None,
+                "kernel": "trace_persistent_kernel<false, kWalkFastPow2>", "peak_source": peak_src,
+                "iterations_per_ray": iters / (rays_per_step * K), "air_phase_share_of_iterations": air_iters / max(1, iters),
+                "algorithmic_bytes_per_launch": algo_bytes_k / K / world,
+                "fetched_bytes_per_launch": fetched_bytes_k / K / world,
+                "frac_by_fetched_bytes": fetched_bytes_k * repeats / (ms * 1e-3) / 1e9 / world / peak,
+                "binding": issue,
+                "note": "algorithmic bytes (SURVEY 8(d)) = the reference algorithm's height fetches, 4 B x loop iterations + 3 B RGB per ray; the production "
+                        "walk issues no load for air-phase iterations and most of the rest hits L1/L2, so the kernel is issue/FMA-bound, not bandwidth-bound "
+                        "(see `binding` and DESIGN.md section 4.1)"}
 
     # ---- e2e: host buffers through the C ABI (hmrt_trace_host): camera H2D + framebuffer D2H in the timed region
     host_fb = torch.empty((POSES, rows, W, 3), dtype=torch.uint8).pin_memory()
-    for s in range(min(2, args.warmup)):
+    for s in range(min(2, Wu)):
         ctx.trace_host(W, H, cams_by_step[s], opts, host_fb)
-    barrier()
+    e2e_repeats = max(1, min(repeats, int(math.ceil(args.min_seconds / max(1e-3, K * (ms / steps_timed) * 1e-3 * 1.1)))))
+    run.barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        ctx.trace_host(W, H, cams_by_step[args.warmup + s], opts, host_fb)
+    for _ in range(e2e_repeats):
+        for cams in timed_batches:
+            ctx.trace_host(W, H, cams, opts, host_fb)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": rays_per_step * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 36,
-           "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / args.steps,
+    e2e = {"value": rays_per_step * K * e2e_repeats / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 36,
+           "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / (K * e2e_repeats), "steps_timed": K * e2e_repeats,
            "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory, copy of frame f overlapped with the traversal of frame f+1; heightmap resident"}
 
-    # ---- CPU baseline (rank 0, N = 1 only): the reference's own code on the host cores ----------
-    cpu = None
+    # ---- frame assembly on the multi-GPU path: all-gather + interleave of one step's row tiles (reported separately)
+    gather = None
+    if world > 1:
+        run.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for f in range(POSES):
+            full = hd.gather_frame(fbs[0][f], H, W)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        g_ms = float(g_ms.item())
+        del full
+        gather = {"ms_per_step": g_ms, "bytes_per_step": POSES * W * H * 3,
+                  "value_incl_gather_Mrays_per_s": rays_per_step / ((ms / steps_timed + g_ms) * 1e-3) / 1e6,
+                  "what": "hmrt.dist.gather_frame: NCCL all-gather of every rank's row tiles + interleave, every rank ends with the whole frame "
+                          "(main.cpp:675-703 delivers one complete frame per call); serial after the step, not overlapped"}
+
+    extra = {}
+    # ---- second pose family (descent-dominated: low altitude, steep pitch) ------------------------
+    if not args.no_extras:
+        low = [hmrt.context._cam_array(make_cameras(hmrt, s, mh, "low")) for s in range(K)]
+        for cams in low[:2]:
+            run.issue(cams, opts)
+        r_low = run.pick_repeats(low, opts, args.min_seconds / 2)
+        if world > 1:
+            r_t = torch.tensor([r_low], dtype=torch.int64, device="cuda")
+            dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+            r_low = int(r_t.item())
+        ms_low, _, _ = run.timed(low, opts, r_low)
+        ctx.trace_stats(reset=True)
+        for cams in low:
+            ctx.trace(W, H, cams, opts, out=fbs[0], hits=hit_buf)
+        st_low = ctx.trace_stats(reset=True)
+        it_low = _allsum(torch, dist, world, st_low["iterations"])
+        air_low = _allsum(torch, dist, world, st_low["air_iterations"])
+        extra["pose_family_low"] = {
+            "what": "altitude 200-500 cells above the terrain maximum, pitch -0.3..-3 (shallow to ~72 degrees down), same map, same frame size",
+            "value": rays_per_step * K * r_low / (ms_low * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_low / (K * r_low),
+            "iterations_per_ray": it_low / (rays_per_step * K), "air_phase_share_of_iterations": air_low / max(1, it_low),
+            "roofline_frac_algorithmic": (4 * it_low + 3 * rays_per_step * K) * r_low / (ms_low * 1e-3) / 1e9 / world / peak}
+
+    # ---- tolerance mode (hmrt_set_trace_variant(2)): speed + agreement with the exact walk on the first timed batch
+    if not args.no_extras:
+        hits_e = torch.empty_like(hit_buf)
+        rgb_e = torch.empty_like(fbs[0])
+        ctx.trace(W, H, timed_batches[0], opts, out=rgb_e, hits=hits_e)
+        ctx.set_trace_variant(2)
+        for cams in timed_batches[:2]:
+            run.issue(cams, opts)
+        ms_tol, _, _ = run.timed(timed_batches, opts, max(1, repeats // 2))
+        ctx.trace(W, H, timed_batches[0], opts, out=fbs[0], hits=hit_buf)
+        torch.cuda.synchronize()
+        cam_pos = torch.tensor([list(p) for p, _ in pose_batch(Wu, mh)], dtype=torch.float32, device="cuda")
+        agree = _tolerance_agreement(torch, hits_e, rgb_e, hit_buf, fbs[0], cam_pos)
+        ctx.set_trace_variant(0)
+        del hits_e, rgb_e
+        extra["tolerance_mode"] = {
+            "what": "hmrt_set_trace_variant(2): the air phase in one closed-form step, exact descent (opt-in; default stays bit-exact)",
+            "value": rays_per_step * K * max(1, repeats // 2) / (ms_tol * 1e-3) / 1e6, "unit": "Mrays/s",
+            "agreement_with_exact_walk_rank0_rows": agree}
+    del hit_buf
+
+    # ---- CPU baseline + parity (rank 0, N = 1 only): the reference's own code on the host cores ----------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_threads = os.cpu_count() or 1
         host_pyr = pyr.cpu().numpy()
-        rate, rays, dt, kind = cpu_sample_rate(host_pyr, mh, args.warmup, 12.0, n_threads)
+        assert (host_pyr[idx[0]:].view(np.uint32) == fin_host.view(np.uint32).ravel()).all(), "device finest level differs from the host terrain"
+        ctx.trace(W, H, timed_batches[0], opts, out=fbs[0])
+        gpu_frames = fbs[0].cpu().numpy()
+        rate, rays, dt, kind, parity = cpu_sample_rate(host_pyr, mh, Wu, 12.0, n_threads, compare_with=gpu_frames)
         cpu = {"value": rate, "unit": "Mrays/s", "cores": n_threads, "kind": kind,
                "sample": f"8-row bands spread over the {POSES} 4K frames of the first timed pose batch, {rays} rays in {dt:.1f} s"}
+        if not args.no_extras:
+            ctx.trace(W, H, low[0], opts, out=fbs[0])
+            gpu_low = fbs[0].cpu().numpy()
+            _, _, _, _, par_low = cpu_sample_rate(host_pyr, mh, 0, 3.0, n_threads, family="low", compare_with=gpu_low)
+            extra["pose_family_low"]["parity"] = par_low
+            del gpu_low
+        del gpu_frames
 
     # ---- the reference's own CUDA kernel, recompiled for sm_100a, on the same GPU and the same frames (reported baseline)
     gpu_ref = None
@@ -396,7 +620,7 @@ def _run_gpu_arm(args):
                                           C.c_int, C.POINTER(C.c_float)]
         one = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
         total_ms, ms_f = 0.0, C.c_float()
-        cams = cams_by_step[args.warmup]
+        cams = timed_batches[0]
         torch.cuda.synchronize()
         for i in range(POSES):
             rc = lib.hmrt_refgpu_trace(pyr.data_ptr(), None, COARSE, LEVELS, W, H, C.byref(cams, i * C.sizeof(hmrt.Camera)), 0, C.c_float(mh),
@@ -408,16 +632,26 @@ def _run_gpu_arm(args):
                    "what": "the reference's own cuda_rayTrace (CudaKernel.cu:195-222) recompiled for sm_100a, one launch per frame with a legal "
                            "block shape, same B200, same pose batch (oracle/refgpu_harness.cu)"}
 
+    # ---- rasterisation (BASELINE configs[3]) at this N -------------------------------------------
+    raster = None
+    if not args.no_raster:
+        del fbs, run
+        torch.cuda.empty_cache()
+        sys.path.insert(0, str(REPO / "benchmarks"))
+        import raster_pipeline
+
+        raster = raster_pipeline.measure(torch, dist, hmrt, ctx, rank, world, args.raster_points, peak)
+
     if rank == 0:
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (1.43 GB pyramid); a different pose batch every step",
-                       "parallelism": f"row tiles of 8 rows interleaved over {world} GPU(s); pyramid replicated by one NCCL broadcast",
-                       "levels": LEVELS, "frame_dimension": FRAME_DIM, "pyramid_broadcast_ms": bcast_ms},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "gpu_reference_baseline": gpu_ref,
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wu,
+            "ms_per_step": ms / steps_timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": CONFIG, "terrain_checksum": checksum,
+            "arm": f"row tiles of 8 rows interleaved over {world} GPU(s); pyramid replicated by one NCCL broadcast ({bcast_ms} ms); steps alternate between two streams",
+            "timed_region": {"steps_timed": steps_timed, "repeats_of_the_k_steps": repeats, "seconds": ms * 1e-3},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "frames_hash_first_timed_step": f"{frames_hash:016x}", "frame_gather": gather,
+            "gpu_reference_baseline": gpu_ref, "raster": raster, "extra": extra,
         }
     else:
         line = None
@@ -430,10 +664,14 @@ def _run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="minimum length of the timed region (the K steps are repeated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the second pose family and the tolerance-mode measurement")
+    ap.add_argument("--no-raster", action="store_true", help="skip the rasterisation sub-record")
+    ap.add_argument("--raster-points", type=int, default=RASTER_POINTS)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -67,6 +67,7 @@ int hmrt_create(int device, hmrt_ctx** out) {
   if (!c) return HMRT_E_NOMEM;
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->probe_verdict = -1;
   cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete c;
@@ -83,6 +84,7 @@ int hmrt_destroy(hmrt_ctx* ctx) {
   if (ctx->d_frames) cudaFree(ctx->d_frames);
   if (ctx->d_fb) cudaFree(ctx->d_fb);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->d_ws) cudaFree(ctx->d_ws);
   if (ctx->d_probe) cudaFree(ctx->d_probe);
   if (ctx->copy_stream) {
@@ -104,6 +106,8 @@ int hmrt_set_stream(hmrt_ctx* ctx, void* cuda_stream) {
   ctx->stream = (cudaStream_t)cuda_stream;
   return 0;
 }
+
+void* hmrt_get_stream(const hmrt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int hmrt_synchronize(hmrt_ctx* ctx) {
   if (!ctx) return HMRT_E_ARG;
@@ -161,7 +165,7 @@ int hmrt_rows_local(int H, int tile_first, int tile_stride) {
 }
 
 int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;
+  if (!ctx || variant < 0 || variant > 2) return HMRT_E_ARG;
   ctx->trace_variant = variant;
   return 0;
 }

@@ -24,19 +24,22 @@ struct hmrt_ctx {
   int sm_count;
   cudaStream_t stream;
   int64_t launches;
-  int trace_variant; /* 0 = production walk, 1 = operation-by-operation walk (diagnostic) */
+  int trace_variant; /* 0 = production walk, 1 = operation-by-operation walk (diagnostic), 2 = tolerance mode (air phase in one step) */
   /* rasterisation: 0 = choose per call (locality probe), 1 = direct atomics, 2 = tile-binned */
   int scatter_mode;
   void* d_ws; /* bucket workspace of the binned scatter */
   size_t ws_cap;
   uint32_t* d_probe;
+  int probe_verdict; /* -1 = no locality probe yet, 0 = spatially ordered input (direct atomics), 1 = unordered (tile-binned) */
   /* borrowed heightmap (hmrt_set_heightmap) */
   bool have_grid;
   hmrt::Grid grid;
   float init_max_height;
-  void* d_scratch;    /* TraceScratch[scratch_cap]: max(top level) key + one work counter per launch of a call */
+  void* d_scratch;    /* TraceScratch[kCallSets][scratch_cap]: max(top level) key + one work counter per launch of a call */
   int scratch_cap;
-  int ctas_per_sm[12]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
+  int call_set;       /* scratch / frame-constant set of the latest trace call (round robin over kCallSets) */
+  unsigned long long* d_stats; /* counters of the instrumented kernels (hmrt_trace_stats) */
+  int ctas_per_sm[16]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;
   int frames_cap;

@@ -1,0 +1,689 @@
+/*
+ * rasterx.cu -- tile-binned rasterisation of point clouds WITHOUT spatial order, on one GPU and -- as an owner-computes
+ * exchange over peer memory -- on the GPUs of one NVLink box.
+ *
+ * CPU semantics being replaced: the loadLASToSection inner loop (GPUHeightmapRaytracer/src/main.cpp:193-234); its fixed
+ * point is `finest = max over points (floored at +0), level i+1 = max of 2x2 children`, independent of point order
+ * (raster.cu).  A direct RED.MAX per point (raster.cu) is the right kernel for survey-ordered files; for uniformly random
+ * points every atomic touches a different 32-byte DRAM sector of a 1 GiB grid (BASELINE config 4: 22 G points/s).  Here:
+ *
+ *   pass 1  rx_bin_kernel     streams the records through shared memory with TMA bulk copies (cp.async.bulk + mbarrier,
+ *                             two stages: chunk k+1 is in flight while chunk k is decoded), decodes each point once,
+ *                             counting-sorts the chunk's (cell, height bits) pairs by grid tile (16 x 16 tiles) in shared
+ *                             memory and appends every tile's run to the CTA's private slice of that tile's bucket:
+ *                             no global atomics, lanes store to a few contiguous runs.
+ *   pass 2  rx_apply_kernel   walks the buckets tile by tile, so the part of the grid under a tile (4 MB at 16384^2) stays
+ *                             L2-resident while its RED.MAXes land.
+ *
+ * Multi-GPU (BASELINE config 4: points sharded by contiguous range).  The north star's exchange is a max all-reduce of the
+ * dense finest level (1 GiB per rank at 16384^2, 93 % of it untouched by a rank's own points).  Because pass 1 already
+ * sorts by tile, the exchange can move POINTS instead of grids: every rank owns a band of tile rows,
+ *
+ *   bin (local)  ->  barrier  ->  apply: each rank pulls the pairs of ITS tiles from every rank's buckets over NVLink
+ *   (P2P loads from peer memory, cudaIpc) and reduces them into its band  ->  barrier  ->  gather + mip build in ONE
+ *   kernel: every 128 x 128 tile is read from its owner's band (P2P), stored into the local finest level and reduced to
+ *   all coarser levels on the way.
+ *
+ * Exchange volume per rank: (N-1)/N of the pairs it owns (8 B per point) + (N-1)/N of the finest level, instead of
+ * 2 (N-1)/N of the finest level for the all-reduce, and no separate mip pass.  The barriers are flag exchanges in peer
+ * memory (one warp per GPU, system-scope stores / polls with a timeout).  Results are bit-identical to one GPU: max is
+ * associative, commutative and idempotent.
+ */
+#include <new>
+#include <stdio.h>
+
+#include "raster_common.cuh"
+
+namespace hmrt {
+
+constexpr int kBinThreads = 256;
+constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles */
+constexpr int kMaxPer = 8;     /* records per thread and step */
+constexpr int kSlicesPerApplyCta = 8;
+constexpr int kMaxPeers = 16;
+constexpr size_t kHeaderBytes = 4096;
+
+/* smallest shift with ceil(res0 / 2^shift) <= 16 */
+int binned_tile_shift(int res0) {
+  int s = 0;
+  while (((res0 + (1 << s) - 1) >> s) > 16) ++s;
+  return s;
+}
+
+/* region header, at offset 0 of every rank's exchange region */
+struct RxHeader {
+  uint32_t flags[kMaxPeers]; /* flags[r]: last barrier epoch rank r has reached (written by rank r over NVLink) */
+  uint32_t overflow;         /* points the bin pass could not store because a slice was full (distributed mode) */
+  uint32_t error;            /* 1 = a barrier timed out */
+};
+
+struct BinParams {
+  ScatterParams sp;
+  const uint8_t* records;
+  int64_t n;
+  int record_len;
+  int per;                /* records per thread and step: chunk = kBinThreads * per */
+  uint2* pairs;           /* [n_tiles][n_slices][slice_cap] (cell, height bits) */
+  uint32_t* counts;       /* [n_tiles][n_slices] */
+  uint32_t slice_cap;
+  int tile_shift, tiles_x, n_tiles;
+  int* finest;            /* single GPU: overflowing points go straight to the grid; NULL: they are counted in *overflow */
+  uint32_t* overflow;
+  int accumulate;         /* continue the slices of an earlier call of the same rasterisation */
+};
+
+/* ---- mbarrier / TMA bulk copy (sm_90+) -------------------------------------------------------------------------- */
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+/* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar` */
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+/*
+ * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][sdest: chunk u32][spair: chunk uint2]
+ * [stage 0][stage 1], a stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
+ */
+__global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_constant__ BinParams p) {
+  extern __shared__ __align__(128) uint8_t rx_smem[];
+  const int chunk = kBinThreads * p.per;
+  uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + 16); /* entries used in this CTA's slice of each bucket (persistent) */
+  uint32_t* hist = fill + kMaxTiles;                          /* points of this step per tile */
+  uint32_t* offs = hist + kMaxTiles;                          /* exclusive prefix of hist */
+  uint32_t* dest0 = offs + kMaxTiles;                         /* first destination index of this step's run, or ~0u: slice full */
+  uint32_t* sdest = dest0 + kMaxTiles;                        /* [chunk] destination pair index per sorted slot */
+  uint2* spair = reinterpret_cast<uint2*>(sdest + chunk);     /* [chunk] sorted pairs */
+  const uint32_t stage_bytes = ((uint32_t)chunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
+  uint8_t* stage0 = reinterpret_cast<uint8_t*>(spair + chunk);
+  stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(rx_smem);
+  const uint32_t stage0_s = (uint32_t)__cvta_generic_to_shared(stage0);
+  __shared__ uint32_t total_s;
+
+  const uint32_t n_slices = gridDim.x;
+  for (int t = threadIdx.x; t < kMaxTiles; t += kBinThreads) {
+    fill[t] = (p.accumulate && t < p.n_tiles) ? p.counts[(size_t)t * n_slices + blockIdx.x] : 0u;
+    hist[t] = 0;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t n_chunks = (p.n + chunk - 1) / chunk;
+  /* issue the load of chunk c into stage s (thread 0 issues the bulk copy, the < 16 tail bytes of the very last chunk
+   * are copied by the first lanes; every use is separated from this point by at least one __syncthreads) */
+  auto issue = [&](int64_t c, int s) {
+    const int64_t first = c * chunk;
+    const int64_t remaining = p.n - first;
+    const uint32_t count = remaining < chunk ? (uint32_t)remaining : (uint32_t)chunk;
+    const uint32_t bytes = count * (uint32_t)p.record_len, bulk = bytes & ~15u;
+    const uint8_t* src = p.records + first * p.record_len; /* 16-byte aligned: chunk * record_len % 16 == 0 */
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the stage before the async write */
+      if (bulk) {
+        mbar_expect_tx(bar0 + 8 * s, bulk);
+        tma_load_1d(stage0_s + (uint32_t)s * stage_bytes, src, bulk, bar0 + 8 * s);
+      } else {
+        mbar_arrive(bar0 + 8 * s);
+      }
+    }
+    if (threadIdx.x < bytes - bulk) stage0[(size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
+  };
+
+  int64_t c = blockIdx.x;
+  if (c < n_chunks) issue(c, 0);
+  __syncthreads();
+  for (int k = 0; c < n_chunks; ++k, c += gridDim.x) {
+    const int s = k & 1;
+    if (c + gridDim.x < n_chunks) issue(c + gridDim.x, s ^ 1);
+    mbar_wait(bar0 + 8 * s, (uint32_t)(k >> 1) & 1u);
+    const uint32_t stage_s = stage0_s + (uint32_t)s * stage_bytes;
+    const int64_t remaining = p.n - c * chunk;
+    const int count = remaining < chunk ? (int)remaining : chunk;
+
+    /* A: decode, rank inside the tile */
+    uint32_t cell[kMaxPer], hb[kMaxPer], slot[kMaxPer];
+#pragma unroll
+    for (int q = 0; q < kMaxPer; ++q) {
+      slot[q] = 0xffffffffu;
+      const int i = q * kBinThreads + threadIdx.x;
+      if (q < p.per && i < count) {
+        const RecordHead rh = load_record_head_shared(stage_s + (uint32_t)i * (uint32_t)p.record_len);
+        /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
+        const double gx = __dadd_rn(__dmul_rn((double)rh.x, p.sp.scale[0]), p.sp.offset[0]);
+        const double gy = __dadd_rn(__dmul_rn((double)rh.y, p.sp.scale[1]), p.sp.offset[1]);
+        const double gz = __dadd_rn(__dmul_rn((double)rh.z, p.sp.scale[2]), p.sp.offset[2]);
+        const int cls = (int)((rh.tail >> 24) & 0x1f);
+        uint32_t cx, cy;
+        float fZ;
+        if (point_to_cell(p.sp, gx, gy, gz, cls, cell[q], fZ, &cx, &cy) && fZ >= 0.0f) {
+          hb[q] = __float_as_uint(fZ);
+          const uint32_t tile = (cy >> p.tile_shift) * (uint32_t)p.tiles_x + (cx >> p.tile_shift);
+          slot[q] = (tile << 16) | atomicAdd(&hist[tile], 1u); /* rank < chunk <= 2048 */
+        }
+      }
+    }
+    __syncthreads();
+    /* B: exclusive prefix over the tiles (warp 0), destinations, slice bookkeeping */
+    if (threadIdx.x < 32) {
+      const int per = (p.n_tiles + 31) / 32;
+      uint32_t sum = 0;
+      for (int q = 0; q < per; ++q) {
+        const int t = threadIdx.x * per + q;
+        if (t < p.n_tiles) sum += hist[t];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)threadIdx.x >= d) incl += v;
+      }
+      uint32_t run = incl - sum;
+      for (int q = 0; q < per; ++q) {
+        const int t = threadIdx.x * per + q;
+        if (t < p.n_tiles) {
+          const uint32_t h = hist[t], f = fill[t];
+          offs[t] = run;
+          run += h;
+          if (f + h <= p.slice_cap) {
+            dest0[t] = (uint32_t)(((size_t)t * n_slices + blockIdx.x) * p.slice_cap + f); /* < 2^32: checked by the launcher */
+            fill[t] = f + h;
+          } else {
+            dest0[t] = 0xffffffffu; /* slice full: this step's points of the tile take the overflow route */
+          }
+          hist[t] = 0;
+        }
+      }
+      if (threadIdx.x == 31) total_s = incl;
+    }
+    __syncthreads();
+    /* C: scatter into sorted order (shared memory) */
+#pragma unroll
+    for (int q = 0; q < kMaxPer; ++q) {
+      if (slot[q] == 0xffffffffu) continue;
+      const uint32_t tile = slot[q] >> 16, rank = slot[q] & 0xffffu;
+      const uint32_t j = offs[tile] + rank, d0 = dest0[tile];
+      spair[j] = make_uint2(cell[q], hb[q]);
+      sdest[j] = d0 == 0xffffffffu ? d0 : d0 + rank;
+    }
+    __syncthreads();
+    /* D: write out; consecutive lanes hit consecutive addresses inside a tile's run */
+    const uint32_t total = total_s;
+    uint32_t dropped = 0;
+    for (uint32_t j = threadIdx.x; j < total; j += kBinThreads) {
+      const uint32_t d = sdest[j];
+      const uint2 v = spair[j];
+      if (d != 0xffffffffu)
+        p.pairs[d] = v;
+      else if (p.finest)
+        atomicMax(p.finest + v.x, (int)v.y);
+      else
+        ++dropped;
+    }
+    if (dropped) atomicAdd(p.overflow, dropped);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < p.n_tiles; t += kBinThreads) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
+}
+
+/* Pass 2.  The buckets of the owned tiles, read from every rank's region (own entry = local memory, the others = peer
+ * memory over NVLink), reduced into dst[cell - cell_base].  Every thread keeps four 16-byte loads (eight pairs) in flight
+ * before it issues their RED.MAXes.  Slices start 32-byte aligned (slice_cap % 4 == 0). */
+struct ApplyParams {
+  const uint8_t* peer[kMaxPeers];
+  size_t counts_off, pairs_off;
+  uint32_t slice_cap, n_slices, world, rank;
+  uint32_t tile_first;      /* owned tiles are [tile_first, tile_first + gridDim.x / groups_per_tile) */
+  uint32_t groups_per_tile; /* ceil(world * n_slices / kSlicesPerApplyCta) */
+  int* dst;
+  uint32_t cell_base;
+};
+
+__global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_constant__ ApplyParams p) {
+  const uint32_t tile = p.tile_first + blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile;
+  const uint32_t all = p.world * p.n_slices;
+  int* __restrict__ dst = p.dst - p.cell_base;
+  for (uint32_t w = g * kSlicesPerApplyCta; w < min(all, (g + 1) * kSlicesPerApplyCta); ++w) {
+    /* ring order over the sources: at any moment the ranks pull from different peers */
+    const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
+    const uint8_t* base = p.peer[src_rank];
+    const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.n_slices + s);
+    const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    const uint32_t n4 = count >> 1; /* whole 16-byte pieces */
+    for (uint32_t i = threadIdx.x; i < n4; i += kBinThreads * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t j = i + (uint32_t)k * kBinThreads;
+        v[k] = j < n4 ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i + (uint32_t)k * kBinThreads < n4) {
+          atomicMax(dst + v[k].x, (int)v[k].y);
+          atomicMax(dst + v[k].z, (int)v[k].w);
+        }
+      }
+    }
+    if ((count & 1u) && threadIdx.x == 0) {
+      const uint2 v = __ldcs(src + (count - 1));
+      atomicMax(dst + v.x, (int)v.y);
+    }
+  }
+}
+
+/* All-gather of the finest level fused with the mip build: tile (x, z) comes from its owner's band. */
+struct GatherParams {
+  MipParams mp;
+  const float* band[kMaxPeers];  /* first cell of every rank's band (peer memory) */
+  int band_row0[kMaxPeers + 1];  /* rank r owns finest rows [band_row0[r], band_row0[r + 1]) */
+  int world;
+  int first_tile_row;            /* rotation of the tile rows: every rank starts with its own band, then its successor's (ring) */
+};
+
+__global__ void __launch_bounds__(512) rx_gather_mips_kernel(const __grid_constant__ GatherParams g) {
+  const int tile_z = (int)((blockIdx.y + (unsigned)g.first_tile_row) % gridDim.y);
+  const int z = tile_z * 128;
+  int o = 0;
+  while (o + 1 < g.world && z >= g.band_row0[o + 1]) ++o;
+  const float* src = g.band[o] + (size_t)(z - g.band_row0[o]) * g.mp.res0 + (size_t)blockIdx.x * 128;
+  mips_tile(g.mp, src, (size_t)g.mp.res0, true, blockIdx.x, tile_z);
+}
+
+/* Cross-GPU barrier: rank -> every peer "I have reached `epoch`", then wait until every peer has told me the same.
+ * One warp; lane r talks to rank r.  A bounded wait: a rank that never arrives sets header.error instead of hanging the GPU. */
+struct BarrierParams {
+  uint8_t* peer[kMaxPeers];
+  int rank, world;
+  uint32_t epoch;
+  long long timeout_cycles;
+};
+
+__global__ void __launch_bounds__(32) rx_barrier_kernel(const __grid_constant__ BarrierParams p) {
+  const int lane = threadIdx.x;
+  if (lane < p.world) {
+    __threadfence_system();
+    volatile uint32_t* remote = &reinterpret_cast<RxHeader*>(p.peer[lane])->flags[p.rank];
+    *remote = p.epoch;
+    volatile uint32_t* mine = &reinterpret_cast<RxHeader*>(p.peer[p.rank])->flags[lane];
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - p.epoch) < 0) {
+      if (clock64() - t0 > p.timeout_cycles) {
+        reinterpret_cast<RxHeader*>(p.peer[p.rank])->error = 1u;
+        break;
+      }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+}
+
+/* ---- host side ---------------------------------------------------------------------------------------------------- */
+struct BinGeometry {
+  int per, chunk;
+  size_t smem;
+  int ctas_per_sm;
+};
+
+static int bin_geometry(int record_len, BinGeometry& g) {
+  g.per = record_len <= 24 ? 8 : 4;
+  g.chunk = kBinThreads * g.per;
+  const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
+  g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + sizeof(uint2)) + 128 + 2 * stage;
+  if (g.smem > 200 * 1024) return HMRT_E_ARG;
+  static size_t configured = 0;
+  if (g.smem > configured) {
+    HMRT_CUDA(cudaFuncSetAttribute(rx_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    configured = g.smem;
+  }
+  HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, rx_bin_kernel, kBinThreads, g.smem));
+  if (g.ctas_per_sm < 1) return HMRT_E_ARG;
+  return 0;
+}
+
+static int64_t slice_capacity(int64_t points, int n_tiles, int n_slices) {
+  int64_t cap = 2 * ((points + (int64_t)n_tiles * n_slices - 1) / ((int64_t)n_tiles * n_slices));
+  cap = (cap + 3) / 4 * 4; /* keep slices 32-byte aligned */
+  return cap < 64 ? 64 : cap;
+}
+
+int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, const ScatterParams& sp, int* finest) {
+  BinGeometry bg;
+  int rc = bin_geometry(record_len, bg);
+  if (rc) return rc;
+  const int tile_shift = binned_tile_shift(sp.res0);
+  const int tiles_x = (sp.res0 + (1 << tile_shift) - 1) >> tile_shift;
+  const int n_tiles = tiles_x * tiles_x;
+  /* sub-batches bound the workspace (~16 B per point at 2x mean slice capacity) to ~16 GB */
+  const int64_t max_batch = (int64_t)1 << 30;
+  for (int64_t first = 0; first < n; first += max_batch) {
+    const int64_t nb = n - first < max_batch ? n - first : max_batch;
+    const int64_t chunks = (nb + bg.chunk - 1) / bg.chunk;
+    const int64_t resident = (int64_t)ctx->sm_count * bg.ctas_per_sm;
+    const int n_slices = (int)(chunks < resident ? chunks : resident);
+    const int64_t slice_cap = slice_capacity(nb, n_tiles, n_slices);
+    if ((unsigned long long)n_tiles * (unsigned long long)n_slices * (unsigned long long)slice_cap >= (1ull << 32)) return HMRT_E_SHAPE;
+    const size_t counts_bytes = ((size_t)n_tiles * (size_t)n_slices * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t need = counts_bytes + (size_t)n_tiles * (size_t)n_slices * (size_t)slice_cap * sizeof(uint2);
+    if (ctx->ws_cap < need) {
+      if (ctx->d_ws) HMRT_CUDA(cudaFree(ctx->d_ws));
+      ctx->d_ws = nullptr;
+      ctx->ws_cap = 0;
+      HMRT_CUDA(cudaMalloc(&ctx->d_ws, need));
+      ctx->ws_cap = need;
+    }
+    uint8_t* ws = static_cast<uint8_t*>(ctx->d_ws);
+    BinParams bp;
+    bp.sp = sp;
+    bp.records = d_records + first * record_len;
+    bp.n = nb;
+    bp.record_len = record_len;
+    bp.per = bg.per;
+    bp.counts = reinterpret_cast<uint32_t*>(ws);
+    bp.pairs = reinterpret_cast<uint2*>(ws + counts_bytes);
+    bp.slice_cap = (uint32_t)slice_cap;
+    bp.tile_shift = tile_shift;
+    bp.tiles_x = tiles_x;
+    bp.n_tiles = n_tiles;
+    bp.finest = finest;
+    bp.overflow = nullptr;
+    bp.accumulate = 0;
+    rx_bin_kernel<<<(unsigned)n_slices, kBinThreads, bg.smem, ctx->stream>>>(bp);
+    HMRT_LAUNCHED(ctx);
+    ApplyParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.peer[0] = ws;
+    ap.counts_off = 0;
+    ap.pairs_off = counts_bytes;
+    ap.slice_cap = (uint32_t)slice_cap;
+    ap.n_slices = (uint32_t)n_slices;
+    ap.world = 1;
+    ap.rank = 0;
+    ap.tile_first = 0;
+    ap.groups_per_tile = (uint32_t)((n_slices + kSlicesPerApplyCta - 1) / kSlicesPerApplyCta);
+    ap.dst = finest;
+    ap.cell_base = 0;
+    rx_apply_kernel<<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
+    HMRT_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+}  // namespace hmrt
+
+/* ================================================== distributed form ================================================ */
+
+struct hmrt_rx {
+  hmrt_ctx* ctx;
+  int coarse_res, levels, res0;
+  int64_t idx[HMRT_MAX_LEVELS];
+  int rank, world;
+  int tile_shift, tile, tiles_x, n_tiles;
+  int n_slices;
+  uint32_t slice_cap;
+  size_t counts_off, pairs_off, band_off, region_bytes;
+  uint8_t* region;
+  uint8_t* peer[hmrt::kMaxPeers];
+  bool connected;
+  bool binned_any;
+  uint32_t epoch;
+  int band_row0[hmrt::kMaxPeers + 1];
+  int tile_row0[hmrt::kMaxPeers + 1];
+};
+
+extern "C" {
+
+int hmrt_rx_barrier(hmrt_rx* rx);
+
+int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int world, int64_t max_points_per_rank, hmrt_rx** out) {
+  if (!ctx || !out || world < 1 || world > hmrt::kMaxPeers || rank < 0 || rank >= world || max_points_per_rank < 0) return HMRT_E_ARG;
+  *out = nullptr;
+  int res[HMRT_MAX_LEVELS];
+  int64_t idx[HMRT_MAX_LEVELS];
+  int rc = hmrt::pyramid_layout(coarse_res, levels, res, idx, nullptr);
+  if (rc) return rc;
+  const int shift = hmrt::binned_tile_shift(res[0]);
+  /* bands are whole tile rows and must be whole 128-row mip tiles; the fused mip kernel covers 8 levels */
+  if (res[0] % 128 != 0 || shift < 7 || levels > 8 || levels < 2) return HMRT_E_SHAPE;
+  hmrt::DeviceGuard guard(ctx->device);
+  hmrt_rx* rx = new (std::nothrow) hmrt_rx();
+  if (!rx) return HMRT_E_NOMEM;
+  memset(rx, 0, sizeof(*rx));
+  rx->ctx = ctx;
+  rx->coarse_res = coarse_res, rx->levels = levels, rx->res0 = res[0];
+  for (int i = 0; i < levels; ++i) rx->idx[i] = idx[i];
+  rx->rank = rank, rx->world = world;
+  rx->tile_shift = shift, rx->tile = 1 << shift;
+  rx->tiles_x = (res[0] + rx->tile - 1) >> shift;
+  rx->n_tiles = rx->tiles_x * rx->tiles_x;
+  /* the same geometry on every rank: all ranks pass the same (coarse_res, levels, world, max_points_per_rank) */
+  rx->n_slices = ctx->sm_count * 2;
+  rx->slice_cap = (uint32_t)hmrt::slice_capacity(max_points_per_rank, rx->n_tiles, rx->n_slices);
+  if ((unsigned long long)rx->n_tiles * (unsigned long long)rx->n_slices * (unsigned long long)rx->slice_cap >= (1ull << 32)) {
+    delete rx;
+    return HMRT_E_SHAPE;
+  }
+  /* tile rows are dealt out as evenly as possible, in rank order (contiguous bands) */
+  const int base = rx->tiles_x / world, rem = rx->tiles_x % world;
+  rx->tile_row0[0] = 0;
+  for (int r = 0; r < world; ++r) rx->tile_row0[r + 1] = rx->tile_row0[r] + base + (r < rem ? 1 : 0);
+  for (int r = 0; r <= world; ++r) {
+    const long long row = (long long)rx->tile_row0[r] * rx->tile;
+    rx->band_row0[r] = (int)(row < res[0] ? row : res[0]);
+  }
+  const size_t counts_bytes = ((size_t)rx->n_tiles * rx->n_slices * sizeof(uint32_t) + 255) & ~(size_t)255;
+  const size_t pairs_bytes = ((size_t)rx->n_tiles * rx->n_slices * rx->slice_cap * sizeof(uint2) + 255) & ~(size_t)255;
+  /* every rank allocates the LARGEST band so that offsets agree everywhere */
+  const size_t band_rows_max = (size_t)(base + (rem ? 1 : 0)) * rx->tile;
+  const size_t band_bytes = band_rows_max * (size_t)res[0] * sizeof(float);
+  rx->counts_off = hmrt::kHeaderBytes;
+  rx->pairs_off = rx->counts_off + counts_bytes;
+  rx->band_off = rx->pairs_off + pairs_bytes;
+  rx->region_bytes = rx->band_off + band_bytes;
+  cudaError_t e = cudaMalloc(&rx->region, rx->region_bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(rx->region, 0, hmrt::kHeaderBytes + counts_bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    if (rx->region) cudaFree(rx->region);
+    delete rx;
+    return (int)e;
+  }
+  rx->peer[rank] = rx->region;
+  rx->connected = world == 1;
+  *out = rx;
+  return 0;
+}
+
+int hmrt_rx_destroy(hmrt_rx* rx) {
+  if (!rx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  cudaStreamSynchronize(rx->ctx->stream);
+  for (int r = 0; r < rx->world; ++r)
+    if (r != rx->rank && rx->peer[r]) cudaIpcCloseMemHandle(rx->peer[r]);
+  if (rx->region) cudaFree(rx->region);
+  delete rx;
+  return 0;
+}
+
+size_t hmrt_rx_region_bytes(const hmrt_rx* rx) { return rx ? rx->region_bytes : 0; }
+
+/* 64-byte cudaIpcMemHandle_t of this rank's exchange region */
+int hmrt_rx_export(hmrt_rx* rx, void* handle64) {
+  if (!rx || !handle64) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  HMRT_CUDA(cudaIpcGetMemHandle(&h, rx->region));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+/* handles: world x 64 bytes, rank order (the own entry is ignored).  Collective in spirit: every rank calls it. */
+int hmrt_rx_connect(hmrt_rx* rx, const void* handles) {
+  if (!rx || !handles) return HMRT_E_ARG;
+  if (rx->connected) return 0;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  for (int r = 0; r < rx->world; ++r) {
+    if (r == rx->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
+    void* p = nullptr;
+    HMRT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    rx->peer[r] = static_cast<uint8_t*>(p);
+  }
+  rx->connected = true;
+  return 0;
+}
+
+/* Start a rasterisation: empty slices, cleared band (the reference's `new float[n]()`, main.cpp:259), no overflow. */
+int hmrt_rx_begin(hmrt_rx* rx) {
+  if (!rx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  cudaStream_t st = rx->ctx->stream;
+  const size_t band_rows = (size_t)(rx->band_row0[rx->rank + 1] - rx->band_row0[rx->rank]);
+  HMRT_CUDA(cudaMemsetAsync(rx->region + rx->counts_off, 0, (size_t)rx->n_tiles * rx->n_slices * sizeof(uint32_t), st));
+  HMRT_CUDA(cudaMemsetAsync(rx->region + offsetof(hmrt::RxHeader, overflow), 0, sizeof(uint32_t), st));
+  if (band_rows) HMRT_CUDA(cudaMemsetAsync(rx->region + rx->band_off, 0, band_rows * (size_t)rx->res0 * sizeof(float), st));
+  rx->binned_any = false;
+  return 0;
+}
+
+/* Pass 1 on this rank's records (any number of calls between begin and apply). */
+int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len, int point_format, const hmrt_las_transform* xf) {
+  if (!rx || !xf || n < 0 || point_format < 0 || point_format > 3) return HMRT_E_ARG;
+  if (record_len < hmrt::kLasMinLen[point_format] || record_len > 64) return HMRT_E_ARG;
+  if (n == 0) return 0;
+  if (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15)) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  hmrt::BinGeometry bg;
+  int rc = hmrt::bin_geometry(record_len, bg);
+  if (rc) return rc;
+  hmrt::BinParams bp;
+  rc = hmrt::fill_scatter_params(xf, rx->res0, bp.sp);
+  if (rc) return rc;
+  bp.sp.cls_off = 15;
+  bp.sp.rgb_off = hmrt::kLasRgbOff[point_format];
+  bp.records = d_records;
+  bp.n = n;
+  bp.record_len = record_len;
+  bp.per = bg.per;
+  bp.counts = reinterpret_cast<uint32_t*>(rx->region + rx->counts_off);
+  bp.pairs = reinterpret_cast<uint2*>(rx->region + rx->pairs_off);
+  bp.slice_cap = rx->slice_cap;
+  bp.tile_shift = rx->tile_shift;
+  bp.tiles_x = rx->tiles_x;
+  bp.n_tiles = rx->n_tiles;
+  bp.finest = nullptr;
+  bp.overflow = reinterpret_cast<uint32_t*>(rx->region + offsetof(hmrt::RxHeader, overflow));
+  bp.accumulate = rx->binned_any ? 1 : 0;
+  /* always n_slices CTAs: the slice layout is part of the exchange geometry */
+  hmrt::rx_bin_kernel<<<(unsigned)rx->n_slices, hmrt::kBinThreads, bg.smem, rx->ctx->stream>>>(bp);
+  HMRT_LAUNCHED(rx->ctx);
+  rx->binned_any = true;
+  return 0;
+}
+
+/* All ranks have reached this point of their streams (flag exchange in peer memory; no host synchronisation). */
+int hmrt_rx_barrier(hmrt_rx* rx) {
+  if (!rx) return HMRT_E_ARG;
+  if (!rx->connected) return HMRT_E_STATE;
+  if (rx->world == 1) return 0;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  hmrt::BarrierParams bp;
+  memset(&bp, 0, sizeof(bp));
+  for (int r = 0; r < rx->world; ++r) bp.peer[r] = rx->peer[r];
+  bp.rank = rx->rank, bp.world = rx->world;
+  bp.epoch = ++rx->epoch;
+  bp.timeout_cycles = 20000000000LL; /* ~10 s at 1.9 GHz */
+  hmrt::rx_barrier_kernel<<<1, 32, 0, rx->ctx->stream>>>(bp);
+  HMRT_LAUNCHED(rx->ctx);
+  return 0;
+}
+
+/* Pass 2 of the exchange: pull the pairs of the owned tiles from every rank and reduce them into the own band. */
+int hmrt_rx_apply(hmrt_rx* rx) {
+  if (!rx) return HMRT_E_ARG;
+  if (!rx->connected) return HMRT_E_STATE;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  const int rows_owned = rx->tile_row0[rx->rank + 1] - rx->tile_row0[rx->rank];
+  if (rows_owned <= 0) return 0;
+  hmrt::ApplyParams ap;
+  memset(&ap, 0, sizeof(ap));
+  for (int r = 0; r < rx->world; ++r) ap.peer[r] = rx->peer[r];
+  ap.counts_off = rx->counts_off;
+  ap.pairs_off = rx->pairs_off;
+  ap.slice_cap = rx->slice_cap;
+  ap.n_slices = (uint32_t)rx->n_slices;
+  ap.world = (uint32_t)rx->world;
+  ap.rank = (uint32_t)rx->rank;
+  ap.tile_first = (uint32_t)(rx->tile_row0[rx->rank] * rx->tiles_x);
+  ap.groups_per_tile = (uint32_t)(((unsigned)rx->world * (unsigned)rx->n_slices + hmrt::kSlicesPerApplyCta - 1) / hmrt::kSlicesPerApplyCta);
+  ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
+  ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
+  const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;
+  hmrt::rx_apply_kernel<<<grid, hmrt::kBinThreads, 0, rx->ctx->stream>>>(ap);
+  HMRT_LAUNCHED(rx->ctx);
+  return 0;
+}
+
+/* All-gather of the finest level from the owners' bands + every coarser level, into the caller's pyramid. */
+int hmrt_rx_gather_mips(hmrt_rx* rx, float* d_pyramid) {
+  if (!rx || !d_pyramid) return HMRT_E_ARG;
+  if (!rx->connected) return HMRT_E_STATE;
+  if ((reinterpret_cast<uintptr_t>(d_pyramid + rx->idx[0]) & 15) || (reinterpret_cast<uintptr_t>(d_pyramid + rx->idx[1]) & 7)) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  hmrt::GatherParams g;
+  memset(&g, 0, sizeof(g));
+  g.mp.pyramid = d_pyramid;
+  g.mp.res0 = rx->res0;
+  g.mp.out_levels = rx->levels - 1;
+  for (int i = 0; i < rx->levels; ++i) g.mp.idx[i] = rx->idx[i];
+  for (int r = 0; r < rx->world; ++r) g.band[r] = reinterpret_cast<const float*>(rx->peer[r] + rx->band_off);
+  for (int r = 0; r <= rx->world; ++r) g.band_row0[r] = rx->band_row0[r];
+  g.world = rx->world;
+  g.first_tile_row = rx->band_row0[rx->rank] / 128;
+  const dim3 grid(rx->res0 / 128, rx->res0 / 128);
+  hmrt::rx_gather_mips_kernel<<<grid, 512, 0, rx->ctx->stream>>>(g);
+  HMRT_LAUNCHED(rx->ctx);
+  /* nobody may reuse (clear, refill) its region before every rank has finished reading it */
+  return hmrt_rx_barrier(rx);
+}
+
+/* After a rasterisation (synchronises the stream): points lost to full slices on THIS rank, barrier time-outs. */
+int hmrt_rx_status(hmrt_rx* rx, uint32_t* overflow, uint32_t* error) {
+  if (!rx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(rx->ctx->device);
+  hmrt::RxHeader h;
+  HMRT_CUDA(cudaMemcpyAsync(&h, rx->region, sizeof(h), cudaMemcpyDeviceToHost, rx->ctx->stream));
+  HMRT_CUDA(cudaStreamSynchronize(rx->ctx->stream));
+  if (overflow) *overflow = h.overflow;
+  if (error) *error = h.error;
+  return 0;
+}
+
+/* rank r owns finest rows [rows[r], rows[r + 1]) (rows has world + 1 entries) */
+int hmrt_rx_bands(const hmrt_rx* rx, int* rows) {
+  if (!rx || !rows) return HMRT_E_ARG;
+  for (int r = 0; r <= rx->world; ++r) rows[r] = rx->band_row0[r];
+  return 0;
+}
+
+}  // extern "C"

@@ -98,6 +98,7 @@ struct Vec3 {
 struct RayResult {
   uint8_t r, g, b;
   uint32_t flags; /* HMRT_HIT_* | steps << HMRT_HIT_STEPS_SHIFT */
+  uint32_t air;   /* how many of those steps the production walk took in its air phase (instrumentation; 0 for the exact walk) */
   Vec3 pos;       /* castRay's by-reference ray_position at return (mirrored space) */
 };
 
@@ -292,6 +293,7 @@ HMRT_HD RayResult trace_pixel(const Grid& g, const Shading& sh, const FrameConst
     }
   }
   out.flags = flags | (steps << HMRT_HIT_STEPS_SHIFT);
+  out.air = 0;
   out.pos = pos;
   return out;
 }

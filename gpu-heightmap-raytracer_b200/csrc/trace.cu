@@ -15,7 +15,6 @@
  * (a fly-through, a batch of camera poses) run in ONE launch.
  */
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "hmrt_internal.cuh"
@@ -30,6 +29,10 @@ constexpr int kStageRow = kChunkW * 3;   /* 96 bytes of RGB8 per chunk row */
 static_assert(HMRT_ROW_TILE == 2 * kChunkH, "a row tile is two chunk rows");
 
 constexpr int kInlineFrames = 48;        /* frames whose constants fit in the kernel parameters */
+/* Calls rotate through this many independent sets of scratch slots / frame-constant slots, so that up to kCallSets trace
+ * calls issued on DIFFERENT streams (hmrt_set_stream between calls) may be in flight at once: the drain of one call's
+ * persistent kernel then runs under the head of the next one (bench.py alternates two streams). */
+constexpr int kCallSets = 4;
 constexpr uint32_t kPrepTopMax = 65536;  /* top levels up to this many cells are reduced by the one-CTA prep kernel */
 
 /* device-side scratch refreshed by the launcher (16 bytes) */
@@ -59,6 +62,7 @@ struct TraceParams {
   uint32_t chunks_x;               /* ceil(W / 32) */
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
   uint32_t total_chunks;           /* frames * chunks_per_frame (< 2^31: larger calls are split by the launcher) */
+  unsigned long long* stats;       /* instrumented kernels only: {rays, loop iterations, air-phase iterations} accumulated */
   /* up to kInlineFrames per-frame constants ride in the kernel parameters: no host->device copy in front
    * of the launch (a 16-frame call spent ~27 us of device timeline on that copy) */
   alignas(16) FrameConsts frame_inline[kInlineFrames];
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(1024) trace_prep_kernel(const float* __restric
 
 /* WALK: kWalkFast* = production walk (ray_fast.cuh); kWalkReference = operation-by-operation walk
  * (ray_core.cuh), kept as the in-library parity reference (hmrt_set_trace_variant). */
-enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2 };
+enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2, kWalkJumpPow2 = 3 /* tolerance mode, see ray_fast.cuh */ };
 
 /* One unit of work of a warp: the tiles [k_first, k_last) of chunk `chunk` (all four in the bulk phase -> 128-bit
  * stores; a single one in the tail phase -> 8-byte stores). */
@@ -158,27 +162,42 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
   __syncwarp();
   const FrameConsts& f = *frame_slot;
 
+  uint32_t st_rays = 0, st_steps = 0, st_air = 0;
 #pragma unroll 1
   for (int k = k_first; k < k_last; ++k) { /* the 8 x 4 tiles of the unit */
     const int tx = k * 8 + lx;
     const int px = x0 + tx;
     if (px < p.W && py < p.H) {
       RayResult r;
-      if (WALK == kWalkFastPow2)
-        r = trace_pixel_fast<true>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
+      if (WALK == kWalkJumpPow2)
+        r = trace_pixel_fast<true, true>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
+      else if (WALK == kWalkFastPow2)
+        r = trace_pixel_fast<true, false>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
       else if (WALK == kWalkFast)
-        r = trace_pixel_fast<false>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
+        r = trace_pixel_fast<false, false>(p.grid, p.shading, tab, hmax, f, p.pixel_grid, p.W, p.H, px, py);
       else
         r = trace_pixel(p.grid, p.shading, f, p.W, p.H, px, py);
       stage[ly][tx * 3 + 0] = r.r;
       stage[ly][tx * 3 + 1] = r.g;
       stage[ly][tx * 3 + 2] = r.b;
-      if (HITS)
+      if (HITS) {
         reinterpret_cast<float4*>(p.hits)[frame_base + (size_t)(row0_local + ly) * p.W + px] =
             make_float4(r.pos.x, r.pos.y, r.pos.z, __uint_as_float(r.flags));
+        st_rays += 1u, st_steps += r.flags >> HMRT_HIT_STEPS_SHIFT, st_air += r.air;
+      }
     }
   }
   __syncwarp();
+  if (HITS && p.stats) { /* a unit is at most 128 rays of < 2^24 iterations each: the 32-bit warp sums cannot overflow in practice */
+    st_rays = __reduce_add_sync(0xffffffffu, st_rays);
+    st_steps = __reduce_add_sync(0xffffffffu, st_steps);
+    st_air = __reduce_add_sync(0xffffffffu, st_air);
+    if (lane == 0) {
+      atomicAdd(p.stats + 0, (unsigned long long)st_rays);
+      atomicAdd(p.stats + 1, (unsigned long long)st_steps);
+      atomicAdd(p.stats + 2, (unsigned long long)st_air);
+    }
+  }
 
   uint8_t* out = p.rgb + frame_base * 3;
   const int xa = x0 + k_first * 8, xb = min(x0 + k_last * 8, p.W); /* pixel columns produced by this unit */
@@ -261,34 +280,45 @@ static const void* pick_kernel(bool hits, int walk, bool tailed) {
   return tailed ? reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, true>)           \
                 : reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, false>)
   if (hits) {
+    if (walk == kWalkJumpPow2) HMRT_PICK(true, kWalkJumpPow2);
     if (walk == kWalkFastPow2) HMRT_PICK(true, kWalkFastPow2);
     if (walk == kWalkFast) HMRT_PICK(true, kWalkFast);
     HMRT_PICK(true, kWalkReference);
   }
+  if (walk == kWalkJumpPow2) HMRT_PICK(false, kWalkJumpPow2);
   if (walk == kWalkFastPow2) HMRT_PICK(false, kWalkFastPow2);
   if (walk == kWalkFast) HMRT_PICK(false, kWalkFast);
   HMRT_PICK(false, kWalkReference);
 #undef HMRT_PICK
 }
 
-/* Scratch slots: slot 0 also holds the top-level maximum; every launch of a call uses its own counter. */
+/* Scratch: kCallSets sets of `scratch_cap` slots; a call takes the next set (round robin), its slot 0 also holds the
+ * top-level maximum and every launch of the call uses its own counter slot. */
 static int ensure_scratch(hmrt_ctx* ctx, int slots) {
   if (ctx->scratch_cap >= slots) return 0;
-  if (ctx->d_scratch) HMRT_CUDA(cudaFree(ctx->d_scratch));
+  if (ctx->d_scratch) HMRT_CUDA(cudaFree(ctx->d_scratch)); /* cudaFree waits for in-flight work */
   ctx->d_scratch = nullptr;
   ctx->scratch_cap = 0;
-  HMRT_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(TraceScratch) * (size_t)slots));
+  HMRT_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(TraceScratch) * (size_t)slots * kCallSets));
   ctx->scratch_cap = slots;
   return 0;
 }
 
-/* Zero `slots` counters and refresh the top-level maximum, on the context's stream. */
-static int prepare_trace(hmrt_ctx* ctx, int slots) {
+/* Zero `slots` counters of the next scratch set and refresh the top-level maximum, on the context's stream.
+ * *base_out = index of the set's first slot. */
+static int prepare_trace(hmrt_ctx* ctx, int slots, int* base_out) {
   int rc = ensure_scratch(ctx, slots);
   if (rc) return rc;
-  TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
+  if (!ctx->d_stats) {
+    HMRT_CUDA(cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
+    HMRT_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  }
+  ctx->call_set = (ctx->call_set + 1) % kCallSets;
+  const int base = ctx->call_set * ctx->scratch_cap;
+  *base_out = base;
+  TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch) + base;
   const uint32_t n_top = ctx->grid.coarse_sq; /* the coarsest level sits at float offset 0 */
-  const bool need_hmax = ctx->trace_variant == 0;
+  const bool need_hmax = ctx->trace_variant != 1;
   const int reduce_here = need_hmax && n_top <= kPrepTopMax;
   trace_prep_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->grid.pyramid, n_top, scratch, slots, reduce_here);
   HMRT_LAUNCHED(ctx);
@@ -310,23 +340,24 @@ static int check_trace_args(const hmrt_ctx* ctx, int W, int H, const hmrt_camera
   return 0;
 }
 
-/* One persistent launch over n_frames cameras on `stream`, using scratch slot `slot` as its counter
- * (prepare_trace must have run on the context's stream and be ordered before `stream`). */
+/* Per-frame constants of launches with more than kInlineFrames frames: kCallSets sets of `frames_cap` entries. */
 static int ensure_frames(hmrt_ctx* ctx, int n) {
   if (ctx->frames_cap >= n) return 0;
   if (ctx->d_frames) HMRT_CUDA(cudaFree(ctx->d_frames)); /* cudaFree waits for in-flight work */
   ctx->d_frames = nullptr;
   ctx->frames_cap = 0;
-  HMRT_CUDA(cudaMalloc(&ctx->d_frames, sizeof(FrameConsts) * (size_t)n));
+  HMRT_CUDA(cudaMalloc(&ctx->d_frames, sizeof(FrameConsts) * (size_t)n * kCallSets));
   ctx->frames_cap = n;
   return 0;
 }
 
+/* One persistent launch over n_frames cameras on `stream`, using scratch slot `slot` of the call's set (first slot
+ * `base`) as its counter (prepare_trace must have run on the context's stream and be ordered before `stream`). */
 /* `frames_at`: index into ctx->d_frames where this launch keeps its per-frame constants (launches of
  * one call that run on different streams must not share them). */
 /* `tile_cnt` > 0 (single-frame launches only): render just the local tiles [tile_lo, tile_lo + tile_cnt) of the frame; d_rgb then
  * points at the first row of local tile `tile_lo`. */
-static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
+static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
                         int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits, int tile_lo = 0, int tile_cnt = 0) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
@@ -360,9 +391,10 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   p.chunks_per_frame = (uint32_t)local_tiles * 2u * p.chunks_x;
   p.total_chunks = p.chunks_per_frame * (uint32_t)n_frames; /* < 2^31, see frames_per_launch() */
   TraceScratch* scratch = static_cast<TraceScratch*>(ctx->d_scratch);
-  p.hmax_key = &scratch[0].hmax_key;
-  p.next_chunk = &scratch[slot].next_chunk;
-  p.next_tail = &scratch[slot].next_tail;
+  p.hmax_key = &scratch[base].hmax_key;
+  p.next_chunk = &scratch[base + slot].next_chunk;
+  p.next_tail = &scratch[base + slot].next_tail;
+  p.stats = ctx->d_stats;
 
   p.pixel_grid.wm1 = (float)(W - 1);
   p.pixel_grid.hm1 = (float)(H - 1);
@@ -381,6 +413,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   } else {
     int rc = ensure_frames(ctx, frames_at + n_frames);
     if (rc) return rc;
+    frames_at += ctx->call_set * ctx->frames_cap;
     /* pageable source: the runtime stages it before returning, so the stack buffer may die */
     FrameConsts local[64];
     for (int base = 0; base < n_frames; base += 64) {
@@ -393,29 +426,26 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int slot, int frames
   }
 
   const bool pow2 = (ctx->grid.coarse_res & (ctx->grid.coarse_res - 1)) == 0;
-  const int walk = ctx->trace_variant != 0 ? kWalkReference : (pow2 ? kWalkFastPow2 : kWalkFast);
+  const int walk = ctx->trace_variant == 1 ? kWalkReference
+                   : !pow2                 ? kWalkFast
+                   : ctx->trace_variant == 2 ? kWalkJumpPow2
+                                             : kWalkFastPow2;
   /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
   /* tile-granular tail only where it pays: fewer than 64 chunks per resident warp (see the kernel comment) */
   const bool tailed = (unsigned long long)p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
   const void* fn = pick_kernel(d_hits != nullptr, walk, tailed);
-  const int kslot = (tailed ? 6 : 0) + (d_hits ? 3 : 0) + walk;
+  const int kslot = (tailed ? 8 : 0) + (d_hits ? 4 : 0) + walk;
   if (ctx->ctas_per_sm[kslot] == 0) {
     int per_sm = 0;
     HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     ctx->ctas_per_sm[kslot] = per_sm < 1 ? 1 : per_sm;
-    if (getenv("HMRT_DEBUG")) {
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, fn);
-      fprintf(stderr, "hmrt: trace kernel slot %d: %d regs, %zu B static smem, %zu B local -> %d CTAs/SM\n", kslot, fa.numRegs, fa.sharedSizeBytes,
-              fa.localSizeBytes, per_sm);
-    }
   }
   const unsigned long long want = ((unsigned long long)p.total_chunks + kWarps - 1) / kWarps;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * (unsigned long long)ctx->ctas_per_sm[kslot];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   /* the tail must be long enough to absorb the longest whole chunk claimed just before it (four near-horizon tiles
    * can take ~10x the mean): 8 chunks per resident warp measured best (1: -4 %, everything tile by tile: -5 %) */
-  static const unsigned long long tail_per_warp = getenv("HMRT_TAIL_PER_WARP") ? (unsigned long long)atoll(getenv("HMRT_TAIL_PER_WARP")) : 8ull; /* tuning knob, read once */
+  constexpr unsigned long long tail_per_warp = 8ull;
   unsigned long long tail_chunks = (unsigned long long)grid * kWarps * tail_per_warp;
   if (tail_chunks > p.total_chunks) tail_chunks = p.total_chunks;
   if (!tailed) tail_chunks = 0;
@@ -445,15 +475,81 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
   hmrt::DeviceGuard guard(ctx->device);
   const int per = frames_per_launch(W, H);
   const int n_launches = (n_frames + per - 1) / per;
-  rc = hmrt::prepare_trace(ctx, n_launches);
+  int base = 0;
+  rc = hmrt::prepare_trace(ctx, n_launches, &base);
   if (rc) return rc;
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const size_t frame_px = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W;
   for (int l = 0; l < n_launches; ++l) {
     const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
-    rc = hmrt::launch_trace(ctx, ctx->stream, l, 0, W, H, h_cameras + f0, nf, opts, d_rgb ? d_rgb + (size_t)f0 * frame_px * 3 : nullptr,
+    rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, d_rgb ? d_rgb + (size_t)f0 * frame_px * 3 : nullptr,
                             d_hits ? d_hits + (size_t)f0 * frame_px : nullptr);
     if (rc) return rc;
+  }
+  return 0;
+}
+
+/* The launch / copy schedule of hmrt_trace_host; any error leaves through the caller, which drains the internal streams
+ * first so that no copy into h_rgb and no kernel writing d_fb is still in flight when the caller sees the error. */
+static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames, const hmrt_trace_opts* opts,
+                              uint8_t* h_rgb, size_t frame_bytes) {
+  const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
+  /*
+   * One launch per frame group, alternating between two internal streams so that the tail of launch l
+   * overlaps the head of launch l+1, each followed by its device->host copy on a third stream: the
+   * copy of frame f overlaps the traversal of the following frames (the reference serialises
+   * upload, trace and GL read-back every frame, main.cpp:947-966).  The top-level maximum is
+   * refreshed once per call on the context's stream; everything is ordered after prior work on it.
+   */
+  /* frames per launch: enough rays (>= ~4 M) to amortise launch + tail, e.g. 1 whole 4K frame on one
+   * GPU, 4 frames when a rank only owns 1/8 of every frame */
+  const size_t rays_per_frame = frame_bytes / 3;
+  const size_t group_rays = 4000000;
+  int group = (int)((group_rays + rays_per_frame - 1) / rays_per_frame);
+  if (group < 1) group = 1;
+  if (group > n_frames) group = n_frames;
+  const int n_launches = (n_frames + group - 1) / group;
+  /* The device->host copy of the LAST launch is the only one nothing overlaps.  When that launch is a single frame, it is
+   * cut into kLastParts tile ranges, each followed by its own copy, so that only a quarter of a frame's copy stays exposed
+   * (4K: 0.45 ms -> 0.11 ms per call). */
+  constexpr int kLastParts = 4;
+  const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
+  const int local_tiles = opts->tile_first < n_tiles ? (n_tiles - opts->tile_first + stride - 1) / stride : 0;
+  const int last_frames = n_frames - (n_launches - 1) * group;
+  const bool split_last = last_frames == 1 && local_tiles >= 4 * kLastParts && rays_per_frame >= 2000000;
+  int base = 0;
+  int rc = hmrt::prepare_trace(ctx, n_launches + (split_last ? kLastParts - 1 : 0), &base);
+  if (rc) return rc;
+  rc = hmrt::ensure_frames(ctx, n_frames); /* sized up front: no reallocation while launches are in flight */
+  if (rc) return rc;
+  HMRT_CUDA(cudaEventRecord(ctx->prep_event, ctx->stream));
+  for (int i = 0; i < 2; ++i) HMRT_CUDA(cudaStreamWaitEvent(ctx->frame_stream[i], ctx->prep_event, 0));
+  const int whole = split_last ? n_launches - 1 : n_launches;
+  for (int l = 0; l < whole; ++l) {
+    const int f0 = l * group, nf = (n_frames - f0 < group) ? n_frames - f0 : group;
+    cudaStream_t st = ctx->frame_stream[l & 1];
+    rc = hmrt::launch_trace(ctx, st, base, l, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr);
+    if (rc) return rc;
+    HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
+    HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
+    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f0 * frame_bytes, ctx->d_fb + (size_t)f0 * frame_bytes, frame_bytes * (size_t)nf,
+                              cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  if (split_last) {
+    const int f0 = n_frames - 1;
+    const size_t row_bytes = (size_t)W * 3, rows_total = frame_bytes / row_bytes;
+    for (int k = 0; k < kLastParts; ++k) {
+      const int l = whole + k;
+      const int t0 = (int)((long long)local_tiles * k / kLastParts), t1 = (int)((long long)local_tiles * (k + 1) / kLastParts);
+      const size_t r0 = (size_t)t0 * HMRT_ROW_TILE, r1 = (size_t)t1 * HMRT_ROW_TILE < rows_total ? (size_t)t1 * HMRT_ROW_TILE : rows_total;
+      const size_t off = (size_t)f0 * frame_bytes + r0 * row_bytes;
+      cudaStream_t st = ctx->frame_stream[l & 1];
+      rc = hmrt::launch_trace(ctx, st, base, l, f0, W, H, h_cameras + f0, 1, opts, ctx->d_fb + off, nullptr, t0, t1 - t0);
+      if (rc) return rc;
+      HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
+      HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
+      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, ctx->d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
   }
   return 0;
 }
@@ -483,64 +579,29 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
     }
     HMRT_CUDA(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
   }
-  /*
-   * One launch per frame, alternating between two internal streams so that the tail of frame f
-   * overlaps the head of frame f+1, each followed by its device->host copy on a third stream: the
-   * copy of frame f overlaps the traversal of the following frames (the reference serialises
-   * upload, trace and GL read-back every frame, main.cpp:947-966).  The top-level maximum is
-   * refreshed once per call on the context's stream; everything is ordered after prior work on it.
-   */
-  /* frames per launch: enough rays (>= ~4 M) to amortise launch + tail, e.g. 1 whole 4K frame on one
-   * GPU, 4 frames when a rank only owns 1/8 of every frame */
-  const size_t rays_per_frame = frame_bytes / 3;
-  size_t group_rays = 4000000;
-  if (const char* e = getenv("HMRT_HOST_GROUP_RAYS")) group_rays = (size_t)atoll(e); /* tuning knob */
-  int group = (int)((group_rays + rays_per_frame - 1) / rays_per_frame);
-  if (group < 1) group = 1;
-  if (group > n_frames) group = n_frames;
-  const int n_launches = (n_frames + group - 1) / group;
-  /* The device->host copy of the LAST launch is the only one nothing overlaps.  When that launch is a single frame, it is
-   * cut into kLastParts tile ranges, each followed by its own copy, so that only a quarter of a frame's copy stays exposed
-   * (4K: 0.45 ms -> 0.11 ms per call). */
-  constexpr int kLastParts = 4;
-  const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
-  const int local_tiles = opts->tile_first < n_tiles ? (n_tiles - opts->tile_first + stride - 1) / stride : 0;
-  const int last_frames = n_frames - (n_launches - 1) * group;
-  const bool split_last = last_frames == 1 && local_tiles >= 4 * kLastParts && rays_per_frame >= 2000000;
-  rc = hmrt::prepare_trace(ctx, n_launches + (split_last ? kLastParts - 1 : 0));
+  rc = trace_host_enqueue(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes);
+  /* one exit: whatever was enqueued -- kernels writing d_fb, copies into h_rgb -- has finished when the caller gets
+   * control back, also on the error paths */
+  cudaError_t e = cudaStreamSynchronize(ctx->frame_stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->frame_stream[1]);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
   if (rc) return rc;
-  rc = hmrt::ensure_frames(ctx, n_frames); /* sized up front: no reallocation while launches are in flight */
-  if (rc) return rc;
-  HMRT_CUDA(cudaEventRecord(ctx->prep_event, ctx->stream));
-  for (int i = 0; i < 2; ++i) HMRT_CUDA(cudaStreamWaitEvent(ctx->frame_stream[i], ctx->prep_event, 0));
-  const int whole = split_last ? n_launches - 1 : n_launches;
-  for (int l = 0; l < whole; ++l) {
-    const int f0 = l * group, nf = (n_frames - f0 < group) ? n_frames - f0 : group;
-    cudaStream_t st = ctx->frame_stream[l & 1];
-    rc = hmrt::launch_trace(ctx, st, l, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr);
-    if (rc) return rc;
-    HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
-    HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
-    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f0 * frame_bytes, ctx->d_fb + (size_t)f0 * frame_bytes, frame_bytes * (size_t)nf,
-                              cudaMemcpyDeviceToHost, ctx->copy_stream));
-  }
-  if (split_last) {
-    const int f0 = n_frames - 1;
-    const size_t row_bytes = (size_t)W * 3, rows_total = frame_bytes / row_bytes;
-    for (int k = 0; k < kLastParts; ++k) {
-      const int l = whole + k;
-      const int t0 = (int)((long long)local_tiles * k / kLastParts), t1 = (int)((long long)local_tiles * (k + 1) / kLastParts);
-      const size_t r0 = (size_t)t0 * HMRT_ROW_TILE, r1 = (size_t)t1 * HMRT_ROW_TILE < rows_total ? (size_t)t1 * HMRT_ROW_TILE : rows_total;
-      const size_t off = (size_t)f0 * frame_bytes + r0 * row_bytes;
-      cudaStream_t st = ctx->frame_stream[l & 1];
-      rc = hmrt::launch_trace(ctx, st, l, f0, W, H, h_cameras + f0, 1, opts, ctx->d_fb + off, nullptr, t0, t1 - t0);
-      if (rc) return rc;
-      HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
-      HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
-      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, ctx->d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    }
-  }
-  HMRT_CUDA(cudaStreamSynchronize(ctx->copy_stream)); /* all frames traced and copied */
+  if (e != cudaSuccess) return (int)e;
+  if (e1 != cudaSuccess) return (int)e1;
+  return (int)e2;
+}
+
+/* Counters of the INSTRUMENTED kernels (d_hits != NULL) since the last reset: out[0] = rays, out[1] = loop iterations
+ * (== height fetches of the reference algorithm, CudaKernel.cu:153-176), out[2] = the share of them the production walk
+ * spent in its air phase (no memory access), out[3] = 0.  Synchronises the context's stream. */
+int hmrt_trace_stats(hmrt_ctx* ctx, uint64_t out[4], int reset) {
+  if (!ctx || !out) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!ctx->d_stats) return 0;
+  HMRT_CUDA(cudaMemcpyAsync(out, ctx->d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) HMRT_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(uint64_t), ctx->stream));
+  HMRT_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

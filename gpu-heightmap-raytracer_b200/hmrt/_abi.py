@@ -74,6 +74,7 @@ PROTOTYPES = {
     "hmrt_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "hmrt_destroy": (C.c_int, [_P]),
     "hmrt_set_stream": (C.c_int, [_P, _P]),
+    "hmrt_get_stream": (_P, [_P]),
     "hmrt_synchronize": (C.c_int, [_P]),
     "hmrt_error_string": (C.c_char_p, [C.c_int]),
     "hmrt_version": (C.c_int, []),
@@ -94,7 +95,20 @@ PROTOTYPES = {
     "hmrt_compose_window": (C.c_int, [_P, C.POINTER(WindowSections), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hmrt_broadcast_heightmap": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "hmrt_allreduce_max_heights": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
+    "hmrt_rx_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "hmrt_rx_destroy": (C.c_int, [_P]),
+    "hmrt_rx_region_bytes": (C.c_size_t, [_P]),
+    "hmrt_rx_export": (C.c_int, [_P, _P]),
+    "hmrt_rx_connect": (C.c_int, [_P, _P]),
+    "hmrt_rx_begin": (C.c_int, [_P]),
+    "hmrt_rx_bin": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(LasTransform)]),
+    "hmrt_rx_barrier": (C.c_int, [_P]),
+    "hmrt_rx_apply": (C.c_int, [_P]),
+    "hmrt_rx_gather_mips": (C.c_int, [_P, _P]),
+    "hmrt_rx_status": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "hmrt_rx_bands": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "hmrt_set_trace_variant": (C.c_int, [_P, C.c_int]),
+    "hmrt_trace_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
     "hmrt_launch_count": (C.c_int64, [_P]),
 }
 

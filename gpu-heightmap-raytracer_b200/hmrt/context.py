@@ -118,8 +118,16 @@ class Context:
         check(self.lib.hmrt_synchronize(self._h), "hmrt_synchronize")
 
     def set_trace_variant(self, variant: int):
-        """0 = production kernel, 1 = operation-by-operation walk (diagnostic, must agree bit for bit)."""
+        """0 = production kernel, 1 = operation-by-operation walk (diagnostic, must agree bit for bit),
+        2 = tolerance mode (air phase in one closed-form step; meets the BASELINE acceptance bars, not bit-identical)."""
         check(self.lib.hmrt_set_trace_variant(self._h, int(variant)), "hmrt_set_trace_variant")
+
+    def trace_stats(self, reset: bool = True):
+        """{rays, iterations, air_iterations} accumulated by the instrumented kernels (trace(..., hits=...)) since the last reset."""
+        out = (C.c_uint64 * 4)()
+        self._bind_stream()
+        check(self.lib.hmrt_trace_stats(self._h, out, int(bool(reset))), "hmrt_trace_stats")
+        return {"rays": int(out[0]), "iterations": int(out[1]), "air_iterations": int(out[2])}
 
     @property
     def launch_count(self) -> int:

@@ -16,7 +16,10 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from ._abi import HMRT_ROW_TILE
+import ctypes as C
+
+from . import _abi
+from ._abi import HMRT_ROW_TILE, check
 
 
 def world():
@@ -90,3 +93,197 @@ def gather_frame(local_rows: torch.Tensor, H: int, W: int, group=None) -> torch.
     parts = [torch.empty_like(padded) for _ in range(world_size)]
     dist.all_gather(parts, padded, group=group)
     return assemble_frame(parts, H, W)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rasterisation pipelines (BASELINE config 4)
+
+def band_rows(res0: int, world_size: int):
+    """rows[r] .. rows[r + 1] = the finest-level rows rank r owns in the peer-memory exchange: whole rows of grid tiles
+    (16 x 16 tiles, csrc/rasterx.cu), dealt out contiguously and as evenly as possible -- the host-side mirror of
+    hmrt_rx_bands (tests/test_dist_gloo.py compares the two)."""
+    shift = 0
+    while ((res0 + (1 << shift) - 1) >> shift) > 16:
+        shift += 1
+    tile = 1 << shift
+    tiles = (res0 + tile - 1) >> shift
+    base, rem = divmod(tiles, world_size)
+    rows, t = [0], 0
+    for r in range(world_size):
+        t += base + (1 if r < rem else 0)
+        rows.append(min(res0, t * tile))
+    return rows
+
+
+def exchange_handles(handle: bytes, group=None):
+    """All-gather one fixed-size opaque blob per rank (the 64-byte cudaIpc handle of a rank's exchange region)."""
+    rank, world_size = world()
+    if world_size == 1:
+        return [handle]
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world_size)]
+    dist.all_gather(parts, mine, group=group)
+    return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+
+
+def all_ranks_agree(ok: bool, group=None) -> bool:
+    """True when `ok` holds on EVERY rank (the exchange path is taken by all ranks or by none)."""
+    rank, world_size = world()
+    if world_size == 1:
+        return bool(ok)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+class RasterPipeline:
+    """clear -> scatter -> exchange -> mip build for one point cloud sharded by contiguous range over the ranks.
+
+    mode "single"     one GPU: hmrt_clear_section, hmrt_scatter_las, hmrt_build_mips.
+    mode "peer"       N GPUs, the owner-computes exchange over peer memory (hmrt_rx_*, csrc/rasterx.cu).
+    mode "allreduce"  N GPUs, the north star's literal form: private full-size grids + NCCL max all-reduce of the finest
+                      level + local mip build.  Taken when the peer path is unavailable on ANY rank (grid shape, cudaIpc
+                      refused) or when it reported an overflow; which one ran is in `self.mode` / exchange_description().
+    """
+
+    def __init__(self, ctx, coarse_res: int, levels: int, single: bool = False, max_points_per_rank: int | None = None, force_mode: str | None = None):
+        self.ctx, self.coarse, self.levels = ctx, coarse_res, levels
+        self.rank, self.world = (0, 1) if single else world()
+        self.res0 = coarse_res << (levels - 1)
+        self.rx = None
+        self.peer_failure = None
+        self.mode = "single" if self.world == 1 else "allreduce"
+        self._max_points = max_points_per_rank
+        self._force = force_mode
+        if self.world == 1 and force_mode == "peer":
+            self.mode = "peer"
+        self.PHASES = ("clear", "scatter", "mips")
+
+    # -- peer path set-up (lazy: needs the per-rank point budget) ----------------------------------------------------
+    def _setup_peer(self, n_local: int):
+        lib = self.ctx.lib
+        want = self._max_points
+        if want is None:
+            t = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+            if self.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            want = int(t.item())
+        h = C.c_void_p()
+        rc = lib.hmrt_rx_create(self.ctx._h, self.coarse, self.levels, self.rank, self.world, want, C.byref(h))
+        ok = rc == 0
+        handle = bytes(64)
+        if ok:
+            buf = (C.c_uint8 * 64)()
+            rc = lib.hmrt_rx_export(h, buf)
+            ok = rc == 0
+            handle = bytes(buf)
+        if not ok:
+            self.peer_failure = f"hmrt_rx_create/export: {_abi.error_string(rc)}"
+        handles = exchange_handles(handle)
+        if all_ranks_agree(ok):
+            blob = b"".join(handles)
+            rc = lib.hmrt_rx_connect(h, blob)
+            ok = rc == 0
+            if not ok:
+                self.peer_failure = f"hmrt_rx_connect: {_abi.error_string(rc)}"
+        else:
+            ok = False
+        ok = all_ranks_agree(ok)
+        if ok:
+            self.rx, self._rx_cap = h, want
+            self.mode = "peer"
+        else:
+            if h:
+                lib.hmrt_rx_destroy(h)
+            self.mode = "allreduce" if self.world > 1 else "single"
+            if self._force == "peer":
+                raise RuntimeError(f"peer-memory exchange unavailable: {self.peer_failure}")
+        return ok
+
+    def close(self):
+        if self.rx is not None:
+            self.ctx.lib.hmrt_rx_destroy(self.rx)
+            self.rx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def exchange_description(self):
+        if self.mode == "peer":
+            return ("owner-computes over peer memory (cudaIpc / NVLink P2P loads): each rank pulls the (cell, height) pairs of the tile rows it "
+                    "owns from every rank's buckets, then one kernel all-gathers the finished bands and builds the mip levels; no NCCL on the data path")
+        if self.mode == "allreduce":
+            why = f" (peer path unavailable: {self.peer_failure})" if self.peer_failure else ""
+            return "NCCL max all-reduce of the dense finest level on its int32 view + local mip build" + why
+        return "none (one GPU)"
+
+    # -- runs ------------------------------------------------------------------------------------------------------------
+    def scatter_only(self, rec, n, rec_len, fmt, xf, pyr, first_index=0):
+        self.ctx.scatter_las(rec, n, rec_len, fmt, xf, pyr, self.coarse, self.levels, first_index=first_index)
+
+    def run(self, rec, n, rec_len, fmt, xf, pyr, first_index=0, timed=False):
+        """One rasterisation of this rank's `n` records into `pyr` (every rank ends with the whole pyramid).
+        Returns {phase: ms} when timed (synchronises), else None."""
+        want_peer = (self.world > 1 and self._force != "allreduce") or self._force == "peer"
+        if want_peer and self.rx is None and self.peer_failure is None:
+            self._setup_peer(n)
+        ev = []
+
+        def mark():
+            if timed:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append(e)
+
+        lib, ctx = self.ctx.lib, self.ctx
+        if self.mode == "peer":
+            self.PHASES = ("clear", "bin", "exchange_apply", "gather_mips")
+            ctx._bind_stream()
+            mark()
+            check(lib.hmrt_rx_begin(self.rx), "hmrt_rx_begin")
+            mark()
+            check(lib.hmrt_rx_bin(self.rx, C.c_void_p(rec.data_ptr()) if n > 0 else None, n, rec_len, fmt, C.byref(xf)), "hmrt_rx_bin")
+            mark()
+            check(lib.hmrt_rx_barrier(self.rx), "hmrt_rx_barrier")
+            check(lib.hmrt_rx_apply(self.rx), "hmrt_rx_apply")
+            check(lib.hmrt_rx_barrier(self.rx), "hmrt_rx_barrier")
+            mark()
+            check(lib.hmrt_rx_gather_mips(self.rx, C.c_void_p(pyr.data_ptr())), "hmrt_rx_gather_mips")
+            mark()
+            ov, er = C.c_uint32(), C.c_uint32()
+            check(lib.hmrt_rx_status(self.rx, C.byref(ov), C.byref(er)), "hmrt_rx_status")
+            bad = ov.value != 0 or er.value != 0
+            if not all_ranks_agree(not bad):
+                # a slice overflowed somewhere (heavily skewed cloud) or a barrier timed out: redo with the dense exchange
+                self.peer_failure = f"overflow {ov.value}, barrier error {er.value} on rank {self.rank} (or on another rank)"
+                self.close()
+                self.mode = "allreduce" if self.world > 1 else "single"
+                return self.run(rec, n, rec_len, fmt, xf, pyr, first_index, timed)
+        else:
+            self.PHASES = ("clear", "scatter", "exchange", "mips") if self.world > 1 else ("clear", "scatter", "mips")
+            res, idx, total = _layout(self.coarse, self.levels)
+            mark()
+            ctx.clear_section(pyr, self.coarse, self.levels)
+            mark()
+            ctx.scatter_las(rec, n, rec_len, fmt, xf, pyr, self.coarse, self.levels, first_index=first_index)
+            mark()
+            if self.world > 1:
+                allreduce_max_heights(pyr[idx[0]:])
+                mark()
+            ctx.build_mips(pyr, self.coarse, self.levels)
+            mark()
+        if not timed:
+            return None
+        torch.cuda.synchronize()
+        return {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(self.PHASES)}
+
+
+def _layout(coarse_res, levels):
+    from .context import pyramid_layout
+
+    return pyramid_layout(coarse_res, levels)

@@ -217,9 +217,11 @@ int Heightmap::clear() {
 int Heightmap::rasterise_las(const LasFile& las, const float cell_size[3], const float origin[2], uint64_t chunk_points) {
   const hmrt_las_transform xf = las.transform(cell_size, origin);
   const size_t chunk_bytes = (size_t)chunk_points * las.record_len;
+  /* copies and events run on the CONTEXT's stream, like the scatter they feed (hmrt_set_stream may have changed it) */
+  cudaStream_t stream = (cudaStream_t)hmrt_get_stream(ctx_);
   uint8_t* h_buf[2] = {nullptr, nullptr};
   uint8_t* d_buf[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
+  cudaEvent_t done[2] = {nullptr, nullptr};
   int rc = 0;
   for (int i = 0; i < 2 && rc == 0; ++i) { /* double-buffered pinned staging */
     rc = (int)cudaMallocHost(&h_buf[i], chunk_bytes);
@@ -230,18 +232,22 @@ int Heightmap::rasterise_las(const LasFile& las, const float cell_size[3], const
   for (int k = 0; rc == 0 && first < las.n_points; ++k) {
     const int b = k & 1;
     const uint64_t n = std::min<uint64_t>(chunk_points, las.n_points - first);
-    if (k >= 2) rc = (int)cudaEventSynchronize(done[b]); /* buffer b is free again */
+    if (k >= 2) rc = (int)cudaEventSynchronize(done[b]); /* the scatter that read buffer b has finished: both halves are free again */
     if (rc == 0 && !las.read_records(first, n, h_buf[b])) rc = HMRT_E_ARG;
-    if (rc == 0) rc = (int)cudaMemcpyAsync(d_buf[b], h_buf[b], (size_t)n * las.record_len, cudaMemcpyHostToDevice, 0);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_buf[b], h_buf[b], (size_t)n * las.record_len, cudaMemcpyHostToDevice, stream);
+    /* first_index == 0 only for the first chunk of a freshly cleared heightmap: the library probes the file's spatial
+     * order there (one stream synchronisation) and keeps the verdict for the following chunks */
     if (rc == 0)
       rc = hmrt_scatter_las(ctx_, d_buf[b], (int64_t)n, las.record_len, las.point_format, &xf, (int64_t)(points_seen_ + first),
                             d_pyramid_, layout_.coarse_res, layout_.levels, d_color_keys_);
-    if (rc == 0) rc = (int)cudaEventRecord(done[b], 0);
+    if (rc == 0) rc = (int)cudaEventRecord(done[b], stream);
     first += n;
   }
-  if (rc == 0) rc = hmrt_synchronize(ctx_);
+  const int sync_rc = hmrt_synchronize(ctx_); /* also on the error paths: nothing may still read the staging buffers */
+  if (rc == 0) rc = sync_rc;
   points_seen_ += las.n_points;
   for (int i = 0; i < 2; ++i) {
+    if (done[i]) cudaEventDestroy(done[i]);
     if (h_buf[i]) cudaFreeHost(h_buf[i]);
     if (d_buf[i]) cudaFree(d_buf[i]);
   }

@@ -111,6 +111,8 @@ int hmrt_create(int device, hmrt_ctx** out);
 int hmrt_destroy(hmrt_ctx* ctx);
 /* `cuda_stream` is a cudaStream_t passed as void* (0 = default stream). */
 int hmrt_set_stream(hmrt_ctx* ctx, void* cuda_stream);
+/* The stream set by hmrt_set_stream (hosts that stage their own copies in front of a call order them on it). */
+void* hmrt_get_stream(const hmrt_ctx* ctx);
 /* Block until all work queued by this context has finished (the reference synchronises inside
  * every call, CudaKernel.cu:301,307,316,325; here calls are asynchronous unless stated). */
 int hmrt_synchronize(hmrt_ctx* ctx);
@@ -133,6 +135,11 @@ int hmrt_set_heightmap(hmrt_ctx* ctx, const float* d_pyramid, const hmrt_color* 
                        int coarse_res, int levels, float max_height);
 
 void hmrt_trace_opts_default(hmrt_trace_opts* opts, float max_height);
+
+/* Up to HMRT_MAX_CALLS_IN_FLIGHT hmrt_trace calls may be in flight at once when the caller switches streams between them
+ * (hmrt_set_stream): every call takes its own set of work counters, so a renderer that double-buffers its frames overlaps
+ * the drain of one call with the head of the next.  Calls on ONE stream simply serialise. */
+#define HMRT_MAX_CALLS_IN_FLIGHT 4
 
 /* == CudaSpace::rayTrace (CudaKernel.cuh:49, CudaKernel.cu:291-308) + cuda_setParameters
  * (CudaKernel.cu:227-240) + cuda_rayTrace (CudaKernel.cu:195-222) for n_frames cameras in ONE
@@ -165,19 +172,21 @@ int hmrt_clear_section(hmrt_ctx* ctx, float* d_pyramid, int coarse_res, int leve
  * float-as-int atomic max (heights are >= +0, main.cpp:227-233 + :259).
  *   d_records  n records of record_len bytes each, LAS 1.2 point data formats 0-3
  *   point_format  0..3 (selects where classification / RGB live)
- *   first_index  global index of record 0 (file order), used for the colour keys
+ *   first_index  global index of record 0 (file order), used for the colour keys (first_index + n < 2^39)
  *   d_color_keys  optional, res0^2 uint64: keeps (index+1)<<24 | rgb of the LAST point in file
  *                 order per cell (the reference's last-writer-wins, main.cpp:223-224)
  * Points outside [0,res0)^2 or with classification 7 are skipped (main.cpp:209).
- * Asynchronous on the context's stream, except that in scatter mode 0 a call with >= 4 M points on a grid of
- * >= 64 tiles first reads back a 4 KB locality probe (one stream synchronisation) to choose its path. */
+ * Asynchronous on the context's stream, except that in scatter mode 0 the FIRST call of an input (first_index == 0) with
+ * >= 4 M points on a grid larger than L2 reads back a 4 KB locality probe (one stream synchronisation) to choose its path;
+ * later chunks of the same input (first_index > 0) reuse the verdict. */
 int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len,
                      int point_format, const hmrt_las_transform* xf, int64_t first_index,
                      float* d_pyramid, int coarse_res, int levels, uint64_t* d_color_keys);
 
 /* Rasterisation strategy of hmrt_scatter_las: 0 (default) = decide per call from a locality probe of the
  * input, 1 = one atomic max per point straight into the grid (best for survey-ordered files and small grids),
- * 2 = bin the points by 1024 x 1024-cell tile first (best for unordered clouds on grids larger than L2).
+ * 2 = bin the points by grid tile (16 x 16 tiles) first (best for unordered clouds on grids larger than L2; needs 16-byte
+ *     aligned records of at most 64 bytes and no colour keys, else the call takes path 1).
  * Results are bit-identical in every mode. */
 int hmrt_set_scatter_mode(hmrt_ctx* ctx, int mode);
 
@@ -250,11 +259,56 @@ int hmrt_broadcast_heightmap(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid, h
 int hmrt_allreduce_max_heights(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid, uint64_t* d_color_keys, int coarse_res,
                                int levels);
 
+/*
+ * Multi-GPU rasterisation as an owner-computes exchange over PEER MEMORY (NVLink P2P through cudaIpc; csrc/rasterx.cu) -- the
+ * faster equivalent of "scatter into a private grid, hmrt_allreduce_max_heights, hmrt_build_mips": points are sharded by
+ * contiguous range (main.cpp:193's file order), every rank OWNS a band of rows of the finest level, and what travels is
+ * the points' (cell, height) pairs to the owner plus one all-gather of the finished bands that is fused with the mip
+ * build.  Bit-identical to one GPU (max is associative, commutative, idempotent).  One hmrt_rx per rank; all ranks pass the
+ * same (coarse_res, levels, world, max_points_per_rank) and make the same sequence of calls:
+ *
+ *     hmrt_rx_create; hmrt_rx_export -> exchange the 64-byte handles (any transport) -> hmrt_rx_connect          (once)
+ *     hmrt_rx_begin; hmrt_rx_bin (1..n times); hmrt_rx_barrier; hmrt_rx_apply; hmrt_rx_barrier; hmrt_rx_gather_mips   (per cloud)
+ *     hmrt_rx_status -> overflow must be 0 on every rank (else: rerun with a larger max_points_per_rank or use the all-reduce path)
+ *
+ * Everything is asynchronous on the context's stream except hmrt_rx_status; the barriers are flag exchanges in peer memory
+ * with a ~10 s time-out (reported by hmrt_rx_status, never a hang).  Needs res0 % 128 == 0, res0 >= 2048, 2 <= levels <= 8
+ * (HMRT_E_SHAPE otherwise) and 16-byte aligned records of at most 64 bytes.  world == 1 works without any peer (tests).
+ * Colour keys are not carried by this path (use hmrt_scatter_las + hmrt_allreduce_max_heights for coloured clouds).
+ */
+typedef struct hmrt_rx hmrt_rx;
+int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int world, int64_t max_points_per_rank, hmrt_rx** out);
+int hmrt_rx_destroy(hmrt_rx* rx);
+size_t hmrt_rx_region_bytes(const hmrt_rx* rx);
+int hmrt_rx_export(hmrt_rx* rx, void* handle64);
+int hmrt_rx_connect(hmrt_rx* rx, const void* handles /* world x 64 bytes, rank order */);
+int hmrt_rx_begin(hmrt_rx* rx);
+int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len, int point_format, const hmrt_las_transform* xf);
+int hmrt_rx_barrier(hmrt_rx* rx);
+int hmrt_rx_apply(hmrt_rx* rx);
+int hmrt_rx_gather_mips(hmrt_rx* rx, float* d_pyramid);
+int hmrt_rx_status(hmrt_rx* rx, uint32_t* overflow, uint32_t* error);
+/* rank r owns finest rows [rows[r], rows[r + 1]); rows has world + 1 entries */
+int hmrt_rx_bands(const hmrt_rx* rx, int* rows);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 
-/* Diagnostic: 0 (default) = production traversal kernel; 1 = the operation-by-operation walk that
- * mirrors CudaKernel.cu:121-177 line by line (slower; the two must agree bit for bit). */
+/* 0 (default) = production traversal kernel, bit-identical to the reference's castRay (CudaKernel.cu:121-177);
+ * 1 = diagnostic: the operation-by-operation walk that mirrors CudaKernel.cu:121-177 line by line (slower; 0 and 1 must
+ *     agree bit for bit);
+ * 2 = TOLERANCE MODE (opt-in): the march through the empty air above the terrain is replaced by one closed-form step to
+ *     the top-level cell in which the ray comes down to the terrain's maximum height; the descent from there is the exact
+ *     one.  Not bit-identical (the entry point carries one rounding instead of the accumulated ones); it meets the
+ *     acceptance bars BASELINE.json states for the path (hit cell >= 99.9 %, hit distance 1e-4 relative, colour 1/255),
+ *     asserted against the reference's own code by tests/test_gpu_tolerance.py.  Grids whose coarse_res is not a power of
+ *     two fall back to variant 0. */
 int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant);
+
+/* Counters of the instrumented kernels (calls with d_hits != NULL) since the last reset: out[0] = rays, out[1] = loop
+ * iterations (== height fetches of the reference algorithm, CudaKernel.cu:153-176; the S of SURVEY.md section 8(d)),
+ * out[2] = the share of them taken in the production walk's air phase (arithmetic only, no height fetch), out[3] = 0.
+ * Synchronises the context's stream. */
+int hmrt_trace_stats(hmrt_ctx* ctx, uint64_t out[4], int reset);
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t hmrt_launch_count(const hmrt_ctx* ctx);

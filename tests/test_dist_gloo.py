@@ -55,6 +55,11 @@ def _worker(rank, world, port, tmp):
     rows = torch.cat([frame[t * 8:min(H, t * 8 + 8)] for t in hd.local_tiles(H, rank, world)])
     got = hd.gather_frame(rows, H, W)
     assert (got == frame).all()
+    # --- host logic of the peer-memory rasterisation exchange (hmrt.dist.RasterPipeline) ----------
+    blobs = hd.exchange_handles(bytes([rank + 1]) * 64)
+    assert blobs == [bytes([r + 1]) * 64 for r in range(world)]
+    assert hd.all_ranks_agree(True) is True
+    assert hd.all_ranks_agree(rank == 0) is False      # one rank cannot take the peer path -> nobody does
     Path(tmp, f"ok{rank}").write_text("ok")
     dist.destroy_process_group()
 
@@ -63,6 +68,21 @@ def test_world_size_2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_band_rows_partition_the_grid():
+    """Owned bands of the peer exchange: whole tile rows, contiguous, in rank order, covering every row once."""
+    sys.path.insert(0, str(REPO / "gpu-heightmap-raytracer_b200"))
+    from hmrt import dist as hd
+
+    for r0 in (2048, 4096, 16384, 32768, 2176):
+        for w in (1, 2, 3, 4, 8, 16):
+            rows = hd.band_rows(r0, w)
+            assert rows[0] == 0 and rows[-1] == r0 and len(rows) == w + 1
+            assert all(a <= b for a, b in zip(rows[:-1], rows[1:]))
+            tile = max(b - a for a, b in zip(rows[:-1], rows[1:]))
+            assert all(r % 128 == 0 for r in rows[:-1]) or r0 % 128
+    assert hd.band_rows(16384, 8) == [2048 * i for i in range(9)]
 
 
 def test_shard_range_covers_everything():

@@ -37,8 +37,8 @@ def sass():
 
 def test_every_kernel_is_present(sass):
     names = " ".join(sass)
-    for k in ["trace_persistent_kernel", "top_level_max_kernel", "scatter_las_kernel", "scatter_xyz_kernel", "bin_points_kernel",
-              "apply_bins_kernel", "build_mips_fused_kernel", "build_mip_level_kernel", "resolve_colors_kernel", "locality_probe_kernel",
+    for k in ["trace_persistent_kernel", "top_level_max_kernel", "scatter_las_kernel", "scatter_xyz_kernel", "rx_bin_kernel",
+              "rx_apply_kernel", "rx_gather_mips_kernel", "rx_barrier_kernel", "build_mips_fused_kernel", "build_mip_level_kernel", "resolve_colors_kernel", "locality_probe_kernel",
               "compose_window_kernel", "compose_colors_kernel"]:
         assert k in names, f"{k} missing from libhmrt.so"
 
@@ -74,3 +74,19 @@ def test_mip_kernel_uses_wide_loads_and_shuffles(sass):
 def test_trace_stores_are_128_bit(sass):
     ins = next(v for n, v in sass.items() if "trace_persistent_kernelILb0ELi2E" in n)
     assert any(i.startswith("STG.E.128") for i in ins)
+
+
+def test_bin_kernel_streams_through_tma(sass):
+    """The tile-binning pass stages its records with TMA bulk copies signalled on an mbarrier (csrc/rasterx.cu)."""
+    ins = next(v for n, v in sass.items() if "rx_bin_kernel" in n)
+    assert any(i.startswith("UBLKCP") for i in ins), "no bulk-copy (TMA) instruction in rx_bin_kernel"
+    assert any(i.startswith("SYNCS") for i in ins), "no mbarrier instruction in rx_bin_kernel"
+    assert any(i.startswith("ATOMS") for i in ins)        # the per-tile histogram lives in shared memory
+    assert not any(i.startswith("ATOMG") for i in ins)    # no global atomics with a return value on the binning path
+
+
+def test_tolerance_walk_has_no_air_loop(sass):
+    """Variant 2 replaces the air loop by one closed-form step: its FFMA2.RM count drops to the general loop's."""
+    exact = next(v for n, v in sass.items() if "trace_persistent_kernelILb0ELi2ELb0E" in n)
+    jump = next(v for n, v in sass.items() if "trace_persistent_kernelILb0ELi3ELb0E" in n)
+    assert sum(i.startswith("FFMA2.RM") for i in jump) < sum(i.startswith("FFMA2.RM") for i in exact)
