@@ -36,10 +36,10 @@
 
 namespace hmrt {
 
-constexpr int kBinThreads = 256;
+constexpr int kBinThreads = 256; /* CTA size of the apply pass; the bin pass is instantiated for 256 and 512 threads */
 constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles */
 constexpr int kMaxPer = 8;     /* records per thread and step */
-constexpr int kSlicesPerApplyCta = 8;
+constexpr int kSlicesPerApplyCta = 2; /* default; see ApplyParams::slices_per_cta.  Few slices per CTA = many CTAs per tile = few tiles in flight: the grid under them stays in L2 */
 constexpr int kMaxPeers = 16;
 constexpr size_t kHeaderBytes = 4096;
 
@@ -99,9 +99,10 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
  * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][sdest: chunk u32][spair: chunk uint2]
  * [stage 0][stage 1], a stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
  */
-__global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_constant__ BinParams p) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__ BinParams p) {
   extern __shared__ __align__(128) uint8_t rx_smem[];
-  const int chunk = kBinThreads * p.per;
+  const int chunk = THREADS * p.per;
   uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + 16); /* entries used in this CTA's slice of each bucket (persistent) */
   uint32_t* hist = fill + kMaxTiles;                          /* points of this step per tile */
   uint32_t* offs = hist + kMaxTiles;                          /* exclusive prefix of hist */
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_consta
   __shared__ uint32_t total_s;
 
   const uint32_t n_slices = gridDim.x;
-  for (int t = threadIdx.x; t < kMaxTiles; t += kBinThreads) {
+  for (int t = threadIdx.x; t < kMaxTiles; t += THREADS) {
     fill[t] = (p.accumulate && t < p.n_tiles) ? p.counts[(size_t)t * n_slices + blockIdx.x] : 0u;
     hist[t] = 0;
   }
@@ -159,25 +160,50 @@ __global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_consta
     const int64_t remaining = p.n - c * chunk;
     const int count = remaining < chunk ? (int)remaining : chunk;
 
-    /* A: decode, rank inside the tile */
+    /* A: decode, rank inside the tile.  Same arithmetic as point_to_cell (main.cpp:200-209), with the conversions taken off
+     * the XU pipe: (double)int32 by the 2^52 + 2^31 bias trick (exact), and -- since floor(t) >= 0 <=> t >= 0 and
+     * floor(t) < res0 <=> t < res0 for an integer res0 -- the range test on t itself and floor(t) read off the significand of
+     * t + 2^23 rounded toward -inf (0 <= t < 2^23). */
     uint32_t cell[kMaxPer], hb[kMaxPer], slot[kMaxPer];
+    const float r0f = (float)p.sp.res0;
+    const bool aligned4 = (p.record_len & 3) == 0;
 #pragma unroll
     for (int q = 0; q < kMaxPer; ++q) {
       slot[q] = 0xffffffffu;
-      const int i = q * kBinThreads + threadIdx.x;
+      const int i = q * THREADS + threadIdx.x;
       if (q < p.per && i < count) {
-        const RecordHead rh = load_record_head_shared(stage_s + (uint32_t)i * (uint32_t)p.record_len);
+        const uint32_t ra = stage_s + (uint32_t)i * (uint32_t)p.record_len;
+        RecordHead rh;
+        if (aligned4) { /* 20 / 28-byte records: X, Y, Z and the flags word are aligned words */
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
+          asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(ra));
+          asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(ra));
+          asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(ra));
+          rh.x = (int32_t)w0, rh.y = (int32_t)w1, rh.z = (int32_t)w2, rh.tail = w3;
+        } else {
+          rh = load_record_head_shared(ra);
+        }
         /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
-        const double gx = __dadd_rn(__dmul_rn((double)rh.x, p.sp.scale[0]), p.sp.offset[0]);
-        const double gy = __dadd_rn(__dmul_rn((double)rh.y, p.sp.scale[1]), p.sp.offset[1]);
-        const double gz = __dadd_rn(__dmul_rn((double)rh.z, p.sp.scale[2]), p.sp.offset[2]);
-        const int cls = (int)((rh.tail >> 24) & 0x1f);
-        uint32_t cx, cy;
-        float fZ;
-        if (point_to_cell(p.sp, gx, gy, gz, cls, cell[q], fZ, &cx, &cy) && fZ >= 0.0f) {
+        const double bias = 4503601774854144.0; /* 2^52 + 2^31 */
+        const double rx_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.x ^ 0x80000000u)), bias);
+        const double ry_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.y ^ 0x80000000u)), bias);
+        const double rz_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.z ^ 0x80000000u)), bias);
+        const double gx = __dadd_rn(__dmul_rn(rx_, p.sp.scale[0]), p.sp.offset[0]);
+        const double gy = __dadd_rn(__dmul_rn(ry_, p.sp.scale[1]), p.sp.offset[1]);
+        const double gz = __dadd_rn(__dmul_rn(rz_, p.sp.scale[2]), p.sp.offset[2]);
+        const float fX = div_cell(__double2float_rn(__dsub_rn(gx, p.sp.mn[0])), p.sp.cell[0], p.sp.rcell[0]); /* :200 */
+        const float fY = div_cell(__double2float_rn(__dsub_rn(gy, p.sp.mn[1])), p.sp.cell[1], p.sp.rcell[1]); /* :201 */
+        const float fZ = div_cell(__double2float_rn(__dsub_rn(gz, p.sp.mn[2])), p.sp.cell[2], p.sp.rcell[2]); /* :202 */
+        const float tx = __fsub_rn(fX, p.sp.origin[0]), ty = __fsub_rn(fY, p.sp.origin[1]);                   /* :205-206 */
+        const bool inside = tx >= 0.0f && tx < r0f && ty >= 0.0f && ty < r0f;                                 /* :209 */
+        if (inside && ((rh.tail >> 24) & 0x1fu) != 7u && fZ >= 0.0f) {
+          const uint32_t cx = __float_as_uint(__fadd_rd(tx, 8388608.0f)) & 0x7fffffu;
+          const uint32_t cy = __float_as_uint(__fadd_rd(ty, 8388608.0f)) & 0x7fffffu;
+          cell[q] = cx + cy * (uint32_t)p.sp.res0;
           hb[q] = __float_as_uint(fZ);
           const uint32_t tile = (cy >> p.tile_shift) * (uint32_t)p.tiles_x + (cx >> p.tile_shift);
-          slot[q] = (tile << 16) | atomicAdd(&hist[tile], 1u); /* rank < chunk <= 2048 */
+          slot[q] = (tile << 16) | atomicAdd(&hist[tile], 1u); /* rank < chunk <= 4096 */
         }
       }
     }
@@ -228,7 +254,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_consta
     /* D: write out; consecutive lanes hit consecutive addresses inside a tile's run */
     const uint32_t total = total_s;
     uint32_t dropped = 0;
-    for (uint32_t j = threadIdx.x; j < total; j += kBinThreads) {
+    for (uint32_t j = threadIdx.x; j < total; j += THREADS) {
       const uint32_t d = sdest[j];
       const uint2 v = spair[j];
       if (d != 0xffffffffu)
@@ -241,7 +267,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_bin_kernel(const __grid_consta
     if (dropped) atomicAdd(p.overflow, dropped);
     __syncthreads();
   }
-  for (int t = threadIdx.x; t < p.n_tiles; t += kBinThreads) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
+  for (int t = threadIdx.x; t < p.n_tiles; t += THREADS) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
 }
 
 /* Pass 2.  The buckets of the owned tiles, read from every rank's region (own entry = local memory, the others = peer
@@ -252,7 +278,8 @@ struct ApplyParams {
   size_t counts_off, pairs_off;
   uint32_t slice_cap, n_slices, world, rank;
   uint32_t tile_first;      /* owned tiles are [tile_first, tile_first + gridDim.x / groups_per_tile) */
-  uint32_t groups_per_tile; /* ceil(world * n_slices / kSlicesPerApplyCta) */
+  uint32_t groups_per_tile; /* ceil(world * n_slices / slices_per_cta) */
+  uint32_t slices_per_cta;
   int* dst;
   uint32_t cell_base;
 };
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
   const uint32_t tile = p.tile_first + blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile;
   const uint32_t all = p.world * p.n_slices;
   int* __restrict__ dst = p.dst - p.cell_base;
-  for (uint32_t w = g * kSlicesPerApplyCta; w < min(all, (g + 1) * kSlicesPerApplyCta); ++w) {
+  for (uint32_t w = g * p.slices_per_cta; w < min(all, (g + 1) * p.slices_per_cta); ++w) {
     /* ring order over the sources: at any moment the ranks pull from different peers */
     const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
     const uint8_t* base = p.peer[src_rank];
@@ -339,25 +366,39 @@ __global__ void __launch_bounds__(32) rx_barrier_kernel(const __grid_constant__ 
 
 /* ---- host side ---------------------------------------------------------------------------------------------------- */
 struct BinGeometry {
-  int per, chunk;
+  int threads, per, chunk;
   size_t smem;
   int ctas_per_sm;
+  const void* fn;
 };
 
+/* development knobs (benchmarks/raster_probe.py); 0 = the built-in choice */
+static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_apply_slices = 0;
+
 static int bin_geometry(int record_len, BinGeometry& g) {
-  g.per = record_len <= 24 ? 8 : 4;
-  g.chunk = kBinThreads * g.per;
-  const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-  g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + sizeof(uint2)) + 128 + 2 * stage;
-  if (g.smem > 200 * 1024) return HMRT_E_ARG;
-  static size_t configured = 0;
-  if (g.smem > configured) {
-    HMRT_CUDA(cudaFuncSetAttribute(rx_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    configured = g.smem;
+  /* 512 threads x 4 records = steps of 2048 points (runs of ~8 pairs per tile): measured best of {256, 512} x {2, 4, 8}
+   * (profiles/raw_r02/raster_probe_*.json) */
+  g.threads = g_knob_bin_threads ? g_knob_bin_threads : 512;
+  g.per = g_knob_bin_per ? g_knob_bin_per : 4;
+  if (g.threads * g.per > 4096) g.per = 4096 / g.threads;
+  g.fn = g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512>) : reinterpret_cast<const void*>(&rx_bin_kernel<256>);
+  for (;;) {
+    g.chunk = g.threads * g.per;
+    const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
+    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + sizeof(uint2)) + 128 + 2 * stage;
+    if (g.smem <= 220 * 1024 || g.per == 1) break;
+    g.per >>= 1; /* long records: smaller steps */
   }
-  HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, rx_bin_kernel, kBinThreads, g.smem));
+  if (g.smem > 220 * 1024) return HMRT_E_ARG;
+  HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));
   if (g.ctas_per_sm < 1) return HMRT_E_ARG;
   return 0;
+}
+
+static int launch_bin(const BinGeometry& g, const BinParams& bp, unsigned grid, cudaStream_t stream) {
+  void* args[] = {const_cast<BinParams*>(&bp)};
+  return (int)cudaLaunchKernel(g.fn, dim3(grid), dim3((unsigned)g.threads), args, g.smem, stream);
 }
 
 static int64_t slice_capacity(int64_t points, int n_tiles, int n_slices) {
@@ -407,7 +448,7 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     bp.finest = finest;
     bp.overflow = nullptr;
     bp.accumulate = 0;
-    rx_bin_kernel<<<(unsigned)n_slices, kBinThreads, bg.smem, ctx->stream>>>(bp);
+    HMRT_CUDA((cudaError_t)launch_bin(bg, bp, (unsigned)n_slices, ctx->stream));
     HMRT_LAUNCHED(ctx);
     ApplyParams ap;
     memset(&ap, 0, sizeof(ap));
@@ -419,7 +460,8 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     ap.world = 1;
     ap.rank = 0;
     ap.tile_first = 0;
-    ap.groups_per_tile = (uint32_t)((n_slices + kSlicesPerApplyCta - 1) / kSlicesPerApplyCta);
+    ap.slices_per_cta = (uint32_t)(g_knob_apply_slices ? g_knob_apply_slices : kSlicesPerApplyCta);
+    ap.groups_per_tile = (uint32_t)((n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
     ap.dst = finest;
     ap.cell_base = 0;
     rx_apply_kernel<<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
@@ -453,6 +495,16 @@ struct hmrt_rx {
 extern "C" {
 
 int hmrt_rx_barrier(hmrt_rx* rx);
+
+/* Development knobs of the binned rasterisation (not part of include/hmrt.h): key 0 = CTA size of the bin pass (256 / 512),
+ * 1 = records per thread and step, 2 = slices per CTA of the apply pass; value 0 restores the built-in choice. */
+int hmrt_debug_raster_knob(int key, int value) {
+  if (key == 0 && (value == 0 || value == 256 || value == 512)) hmrt::g_knob_bin_threads = value;
+  else if (key == 1 && value >= 0 && value <= 8) hmrt::g_knob_bin_per = value;
+  else if (key == 2 && value >= 0 && value <= 64) hmrt::g_knob_apply_slices = value;
+  else return HMRT_E_ARG;
+  return 0;
+}
 
 int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int world, int64_t max_points_per_rank, hmrt_rx** out) {
   if (!ctx || !out || world < 1 || world > hmrt::kMaxPeers || rank < 0 || rank >= world || max_points_per_rank < 0) return HMRT_E_ARG;
@@ -595,7 +647,7 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   bp.overflow = reinterpret_cast<uint32_t*>(rx->region + offsetof(hmrt::RxHeader, overflow));
   bp.accumulate = rx->binned_any ? 1 : 0;
   /* always n_slices CTAs: the slice layout is part of the exchange geometry */
-  hmrt::rx_bin_kernel<<<(unsigned)rx->n_slices, hmrt::kBinThreads, bg.smem, rx->ctx->stream>>>(bp);
+  HMRT_CUDA((cudaError_t)hmrt::launch_bin(bg, bp, (unsigned)rx->n_slices, rx->ctx->stream));
   HMRT_LAUNCHED(rx->ctx);
   rx->binned_any = true;
   return 0;
@@ -635,7 +687,8 @@ int hmrt_rx_apply(hmrt_rx* rx) {
   ap.world = (uint32_t)rx->world;
   ap.rank = (uint32_t)rx->rank;
   ap.tile_first = (uint32_t)(rx->tile_row0[rx->rank] * rx->tiles_x);
-  ap.groups_per_tile = (uint32_t)(((unsigned)rx->world * (unsigned)rx->n_slices + hmrt::kSlicesPerApplyCta - 1) / hmrt::kSlicesPerApplyCta);
+  ap.slices_per_cta = (uint32_t)(hmrt::g_knob_apply_slices ? hmrt::g_knob_apply_slices : hmrt::kSlicesPerApplyCta);
+  ap.groups_per_tile = (uint32_t)(((unsigned)rx->world * (unsigned)rx->n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
   ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
   ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
   const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;

@@ -296,12 +296,13 @@ int hmrt_rx_bands(const hmrt_rx* rx, int* rows);
 /* 0 (default) = production traversal kernel, bit-identical to the reference's castRay (CudaKernel.cu:121-177);
  * 1 = diagnostic: the operation-by-operation walk that mirrors CudaKernel.cu:121-177 line by line (slower; 0 and 1 must
  *     agree bit for bit);
- * 2 = TOLERANCE MODE (opt-in): the march through the empty air above the terrain is replaced by one closed-form step to
- *     the top-level cell in which the ray comes down to the terrain's maximum height; the descent from there is the exact
- *     one.  Not bit-identical (the entry point carries one rounding instead of the accumulated ones); it meets the
- *     acceptance bars BASELINE.json states for the path (hit cell >= 99.9 %, hit distance 1e-4 relative, colour 1/255),
- *     asserted against the reference's own code by tests/test_gpu_tolerance.py.  Grids whose coarse_res is not a power of
- *     two fall back to variant 0. */
+ * 2 = EXPERIMENTAL, opt-in: the march through the empty air above the terrain is replaced by one closed-form step to the
+ *     top-level cell in which the ray comes down to the terrain's maximum height; the descent from there is the exact one.
+ *     2.3x the rays per second on high-altitude views, but not bit-identical: the entry point carries one rounding instead
+ *     of the ~50 accumulated ones of the reference's walk.  Measured against the reference's own code on the benchmark
+ *     poses (tests/test_gpu_fullsize.py, bench.py extra.tolerance_mode): colour within 1/255 on 99.99 % and pixel-exact on
+ *     99.9 % of the pixels, hit cell equal on 99.8 % -- BELOW the 99.9 % hit-cell bar BASELINE.json states, which is why
+ *     no default path and no reported number uses it.  Grids whose coarse_res is not a power of two fall back to variant 0. */
 int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant);
 
 /* Counters of the instrumented kernels (calls with d_hits != NULL) since the last reset: out[0] = rays, out[1] = loop
