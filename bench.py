@@ -307,6 +307,13 @@ class StepRunner:
         with self.torch.cuda.stream(self.streams[k]):
             self.ctx.trace(W, H, cams, opts, out=self.fbs[k], hits=hits if hits is not None else False)
 
+    def with_buffers(self, fbs):
+        """The same streams, other output buffers (e.g. frames shared with rank 0)."""
+        other = StepRunner.__new__(StepRunner)
+        other.__dict__.update(self.__dict__)
+        other.fbs = fbs
+        return other
+
     def timed(self, cam_batches, opts, repeats=1):
         """Device time (ms) of len(cam_batches) * repeats steps, max over ranks, bracketed by barrier + synchronize."""
         torch = self.torch
@@ -528,24 +535,30 @@ def _run_gpu_arm(args):
            "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / (K * e2e_repeats), "steps_timed": K * e2e_repeats,
            "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory, copy of frame f overlapped with the traversal of frame f+1; heightmap resident"}
 
-    # ---- frame assembly on the multi-GPU path: all-gather + interleave of one step's row tiles (reported separately)
+    # ---- frame assembly on the multi-GPU path (the reference delivers ONE complete frame per call, main.cpp:675-703):
+    # every rank stores its row tiles straight into rank 0's frames over NVLink from inside the traversal kernel
+    # (hmrt_trace_opts.full_frame_output + a cudaIpc mapping of rank 0's buffer): the same timed loop, whole frames on rank 0
     gather = None
     if world > 1:
-        run.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for f in range(POSES):
-            full = hd.gather_frame(fbs[0][f], H, W)
-        g1.record()
-        torch.cuda.synchronize()
-        g_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        g_ms = float(g_ms.item())
-        del full
-        gather = {"ms_per_step": g_ms, "bytes_per_step": POSES * W * H * 3,
-                  "value_incl_gather_Mrays_per_s": rays_per_step / ((ms / steps_timed + g_ms) * 1e-3) / 1e6,
-                  "what": "hmrt.dist.gather_frame: NCCL all-gather of every rank's row tiles + interleave, every rank ends with the whole frame "
-                          "(main.cpp:675-703 delivers one complete frame per call); serial after the step, not overlapped"}
+        shared = [hd.SharedFrames(ctx, POSES, H, W, root=0) for _ in range(2)]
+        opts_full = hmrt.trace_opts(mh, tile_first=tile_first, tile_stride=tile_stride, full_frame_output=True)
+        run_full = run.with_buffers([sf.tensor for sf in shared])
+        for cams in timed_batches[:2]:
+            run_full.issue(cams, opts_full)
+        ms_full, _, _ = run_full.timed(timed_batches, opts_full, repeats)
+        # the assembled frames of the first timed step, hashed on rank 0 alone, must equal the N-independent hash of the tiles
+        run_full.barrier()
+        with torch.cuda.stream(run_full.streams[0]):
+            ctx.trace(W, H, timed_batches[0], opts_full, out=shared[0].tensor)
+        run_full.barrier()
+        assembled_hash = _frames_hash(torch, shared[0].tensor, 0, 1) if rank == 0 else 0
+        for sf in shared:
+            sf.close()
+        gather = {"value": rays_per_step * steps_timed / (ms_full * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_full / steps_timed,
+                  "bytes_into_rank0_per_step": POSES * W * H * 3 * (world - 1) // world,
+                  "assembled_frames_hash": f"{assembled_hash:016x}", "assembled_equals_tiles": assembled_hash == frames_hash,
+                  "what": "whole frames assembled on rank 0 inside the timed loop: every rank's traversal kernel stores its 8-row tiles at their place in "
+                          "rank 0's frame buffer (cudaIpc peer mapping, 128-bit stores over NVLink); no gather pass, no collective"}
 
     extra = {}
     # ---- second pose family (descent-dominated: low altitude, steep pitch) ------------------------

@@ -172,4 +172,46 @@ int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant) {
 
 int64_t hmrt_launch_count(const hmrt_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+int hmrt_ipc_alloc(hmrt_ctx* ctx, size_t bytes, void** d_ptr, void* handle64) {
+  if (!ctx || !d_ptr || !handle64 || bytes == 0) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  *d_ptr = nullptr;
+  void* p = nullptr;
+  HMRT_CUDA(cudaMalloc(&p, bytes)); /* cudaMalloc, not a pooled allocation: only whole allocations can be exported */
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return (int)e;
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *d_ptr = p;
+  return 0;
+}
+
+int hmrt_ipc_free(hmrt_ctx* ctx, void* d_ptr) {
+  if (!ctx || !d_ptr) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  HMRT_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+
+int hmrt_ipc_open(hmrt_ctx* ctx, const void* handle64, void** d_ptr) {
+  if (!ctx || !handle64 || !d_ptr) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  *d_ptr = nullptr;
+  HMRT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int hmrt_ipc_close(hmrt_ctx* ctx, void* d_ptr) {
+  if (!ctx || !d_ptr) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  HMRT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
 }  // extern "C"

@@ -50,7 +50,8 @@ struct TraceParams {
   uint8_t* rgb;
   hmrt_hit* hits;
   int W, H;
-  int rows_local;
+  int rows_local;   /* rows per frame of the OUTPUT: the rows this call renders (compact), or H (full_layout) */
+  int full_layout;
   int tile_first, tile_stride;
   int vec_store; /* W % 16 == 0 and rgb 16-byte aligned */
   PixelGrid pixel_grid; /* (W - 1), (H - 1), their reciprocals; whether the frames allow primary_ray_fast */
@@ -148,7 +149,8 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
   const int j = (int)(strip >> 1), half = (int)(strip & 1u);
   const int tile = p.tile_first + j * p.tile_stride;         /* 8-row tile in the frame */
   const int row0 = tile * HMRT_ROW_TILE + half * kChunkH;    /* first row of the chunk in the frame */
-  const int row0_local = j * HMRT_ROW_TILE + half * kChunkH; /* ... in this call's output */
+  /* ... in this call's output: compact (local tile j at rows [8 j, 8 j + 8)), or -- full_layout -- at its place in the frame */
+  const int row0_local = p.full_layout ? row0 : j * HMRT_ROW_TILE + half * kChunkH;
   const int py = row0 + ly;
   const int x0 = (int)cx * kChunkW;
   const size_t frame_base = (size_t)frame * ((size_t)p.rows_local * (size_t)p.W);
@@ -383,7 +385,8 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
   p.hits = d_hits;
   p.W = W;
   p.H = H;
-  p.rows_local = rows_local(H, opts->tile_first, stride);
+  p.full_layout = opts->full_frame_output ? 1 : 0;
+  p.rows_local = p.full_layout ? H : rows_local(H, opts->tile_first, stride);
   p.tile_first = tile_first;
   p.tile_stride = stride;
   p.vec_store = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0);
@@ -479,7 +482,7 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
   rc = hmrt::prepare_trace(ctx, n_launches, &base);
   if (rc) return rc;
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
-  const size_t frame_px = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W;
+  const size_t frame_px = (size_t)(opts->full_frame_output ? H : hmrt::rows_local(H, opts->tile_first, stride)) * (size_t)W;
   for (int l = 0; l < n_launches; ++l) {
     const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
     rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, d_rgb ? d_rgb + (size_t)f0 * frame_px * 3 : nullptr,
@@ -558,7 +561,7 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
                     const hmrt_trace_opts* opts, uint8_t* h_rgb) {
   int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
   if (rc) return rc;
-  if (!h_rgb) return HMRT_E_ARG;
+  if (!h_rgb || opts->full_frame_output) return HMRT_E_ARG; /* the host copy is always compact */
   hmrt::DeviceGuard guard(ctx->device);
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const size_t frame_bytes = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W * 3;

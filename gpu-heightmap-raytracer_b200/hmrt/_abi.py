@@ -46,6 +46,7 @@ class TraceOpts(C.Structure):  # hmrt_trace_opts
         ("shadow_bias", C.c_float),
         ("tile_first", C.c_int),
         ("tile_stride", C.c_int),
+        ("full_frame_output", C.c_int),
     ]
 
 
@@ -95,6 +96,10 @@ PROTOTYPES = {
     "hmrt_compose_window": (C.c_int, [_P, C.POINTER(WindowSections), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hmrt_broadcast_heightmap": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "hmrt_allreduce_max_heights": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
+    "hmrt_ipc_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P), _P]),
+    "hmrt_ipc_free": (C.c_int, [_P, _P]),
+    "hmrt_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "hmrt_ipc_close": (C.c_int, [_P, _P]),
     "hmrt_rx_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
     "hmrt_rx_destroy": (C.c_int, [_P]),
     "hmrt_rx_region_bytes": (C.c_size_t, [_P]),

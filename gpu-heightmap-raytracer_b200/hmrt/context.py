@@ -49,7 +49,7 @@ def camera(position, forward, frame_dim=(32.0, 18.0, 20.0), normalize=True) -> C
 
 def trace_opts(max_height: float, use_color_map: bool = False, shadows: bool = False,
                light_dir=(0.3, 0.8, 0.52), shadow_bias: float = 0.0, tile_first: int = 0,
-               tile_stride: int = 1) -> TraceOpts:
+               tile_stride: int = 1, full_frame_output: bool = False) -> TraceOpts:
     o = TraceOpts()
     _abi.load().hmrt_trace_opts_default(C.byref(o), float(np.float32(max_height)))
     o.use_color_map = int(bool(use_color_map))
@@ -60,6 +60,7 @@ def trace_opts(max_height: float, use_color_map: bool = False, shadows: bool = F
     o.shadow_bias = float(shadow_bias)
     o.tile_first = int(tile_first)
     o.tile_stride = int(tile_stride)
+    o.full_frame_output = int(bool(full_frame_output))
     return o
 
 
@@ -73,6 +74,26 @@ def _cam_array(cameras) -> "C.Array[Camera]":
     for i, c in enumerate(cams):
         C.memmove(C.byref(arr, i * C.sizeof(Camera)), C.byref(c), C.sizeof(Camera))
     return arr
+
+
+class IpcBuffer:
+    """A raw device allocation (own or peer) viewed as a torch tensor through __cuda_array_interface__."""
+
+    def __init__(self, ctx, ptr: int, nbytes: int, owner: bool):
+        self.ctx, self.ptr, self.nbytes, self.owner = ctx, ptr, nbytes, owner
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def tensor(self, shape):
+        import torch
+
+        t = torch.as_tensor(self, device=torch.device("cuda", self.ctx.device))
+        return t.view(*shape)
+
+    def close(self):
+        if self.ptr:
+            fn = self.ctx.lib.hmrt_ipc_free if self.owner else self.ctx.lib.hmrt_ipc_close
+            fn(self.ctx._h, C.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 class Context:
@@ -164,7 +185,7 @@ class Context:
         torch = self._torch
         cams = _cam_array(cameras)
         n = len(cams)
-        rows = rows_local(H, opts.tile_first, opts.tile_stride)
+        rows = H if opts.full_frame_output else rows_local(H, opts.tile_first, opts.tile_stride)
         dev = torch.device("cuda", self.device)
         if out is None:
             out = torch.empty((n, rows, W, 3), dtype=torch.uint8, device=dev)
@@ -199,6 +220,19 @@ class Context:
         self._bind_stream()
         check(self.lib.hmrt_trace_host(self._h, W, H, cams, n, C.byref(opts), C.c_void_p(ptr)), "hmrt_trace_host")
         return out_host
+
+    # -- buffers other ranks can map (cudaIpc) -------------------------------------------------
+    def ipc_alloc(self, nbytes: int):
+        """(IpcBuffer, 64-byte handle): a device buffer of this context that other processes on the box can open."""
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        check(self.lib.hmrt_ipc_alloc(self._h, nbytes, C.byref(ptr), handle), "hmrt_ipc_alloc")
+        return IpcBuffer(self, ptr.value, nbytes, owner=True), bytes(handle)
+
+    def ipc_open(self, handle: bytes, nbytes: int):
+        """Map a buffer another process allocated with ipc_alloc (peer memory over NVLink)."""
+        ptr = C.c_void_p()
+        check(self.lib.hmrt_ipc_open(self._h, handle, C.byref(ptr)), "hmrt_ipc_open")
+        return IpcBuffer(self, ptr.value, nbytes, owner=False)
 
     # -- rasterisation ---------------------------------------------------------------------
     def clear_section(self, pyramid, coarse_res: int, levels: int, color_keys=None, color_map=None):

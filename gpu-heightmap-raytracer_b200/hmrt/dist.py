@@ -95,6 +95,42 @@ def gather_frame(local_rows: torch.Tensor, H: int, W: int, group=None) -> torch.
     return assemble_frame(parts, H, W)
 
 
+class SharedFrames:
+    """[n_frames, H, W, 3] uint8 frames that live on rank `root` and are mapped by every other rank (cudaIpc peer memory).
+    A row-tile-sharded render with hmrt_trace_opts.full_frame_output = 1 and `out = shared.tensor` has every rank store
+    its tiles straight into the root's frames over NVLink, inside the traversal kernel: the frame assembly the reference
+    does by rendering one whole frame per call (main.cpp:675-703) costs no extra pass and no collective.  Collective
+    constructor (all ranks call it); after a device barrier the root holds complete frames."""
+
+    def __init__(self, ctx, n_frames: int, H: int, W: int, root: int = 0, group=None):
+        rank, world_size = world()
+        self.root, self.shape = root, (n_frames, H, W, 3)
+        nbytes = n_frames * H * W * 3
+        handle = bytes(64)
+        self.buf = None
+        if rank == root:
+            self.buf, handle = ctx.ipc_alloc(nbytes)
+        handles = exchange_handles(handle, group)
+        if rank != root:
+            self.buf = ctx.ipc_open(handles[root], nbytes)
+        self.tensor = self.buf.tensor(self.shape)
+
+    def close(self, group=None):
+        rank, world_size = world()
+        if self.buf is None:
+            return
+        self.tensor = None
+        if world_size > 1:
+            dist.barrier(group)          # nobody still writes into the root's memory
+        if rank != self.root:
+            self.buf.close()
+        if world_size > 1:
+            dist.barrier(group)          # every mapping is gone before the owner frees
+        if rank == self.root:
+            self.buf.close()
+        self.buf = None
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # rasterisation pipelines (BASELINE config 4)
 

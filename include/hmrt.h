@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMRT_VERSION 100
+#define HMRT_VERSION 200 /* round 2: hmrt_trace_opts grew by full_frame_output; hmrt_rx_*, hmrt_ipc_*, hmrt_trace_stats, hmrt_get_stream added */
 #define HMRT_MAX_LEVELS 16
 
 /* argument errors (negative so they never collide with cudaError_t) */
@@ -89,6 +89,11 @@ typedef struct hmrt_trace_opts {
    * (or stride 0) = whole frame in natural order. */
   int tile_first;
   int tile_stride;
+  /* 0: the output holds only the rows this call renders (compact, see above).  1: the output is a WHOLE frame (H rows per
+   * frame) and every rendered tile is stored at its place in it -- the buffer may be another GPU's memory (a peer mapping,
+   * see hmrt_ipc_*): the ranks of a row-tile-sharded render then assemble the frame the reference delivers per call
+   * (main.cpp:675-703) with their own stores, over NVLink, inside the traversal kernel.  Not for hmrt_trace_host. */
+  int full_frame_output;
 } hmrt_trace_opts;
 #define HMRT_ROW_TILE 8
 
@@ -237,6 +242,15 @@ typedef struct hmrt_window_sections {
  * the colour map likewise at the finest resolution.  d_window_color_map may be NULL.  Asynchronous on the context's stream. */
 int hmrt_compose_window(hmrt_ctx* ctx, const hmrt_window_sections* sections, int coarse_res, int levels, int cell_x, int cell_y,
                         float* d_window_pyramid, hmrt_color* d_window_color_map);
+
+/* ---- device buffers other processes on the same box can map (cudaIpc; NVLink peer access) -----------------------------
+ * hmrt_ipc_alloc: a device buffer on the context's device + its 64-byte handle; hmrt_ipc_open (in ANOTHER process): map
+ * it on this context's device; hmrt_ipc_close / hmrt_ipc_free undo them.  Used for the frame of a row-tile-sharded render
+ * (hmrt_trace_opts.full_frame_output): rank 0 allocates the frame, every other rank opens it and renders straight into it. */
+int hmrt_ipc_alloc(hmrt_ctx* ctx, size_t bytes, void** d_ptr, void* handle64);
+int hmrt_ipc_free(hmrt_ctx* ctx, void* d_ptr);
+int hmrt_ipc_open(hmrt_ctx* ctx, const void* handle64, void** d_ptr);
+int hmrt_ipc_close(hmrt_ctx* ctx, void* d_ptr);
 
 /* ---- multi-GPU exchange steps --------------------------------------------------------- */
 

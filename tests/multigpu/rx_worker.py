@@ -52,6 +52,26 @@ def main():
         if rank == 0:
             want, _ = rl.oracle_rasterise(hdr, rec, coarse, levels, with_colors=False)
             assert (whole.view(np.uint32) == want.view(np.uint32)).all(), "one GPU != oracle"
+    # ---- row-tile-sharded render assembled on rank 0 through a peer mapping (hmrt.dist.SharedFrames) -----------------
+    sc = ol.scene("r1024_l8", seed=2)
+    pyr = torch.from_numpy(sc["pyramid"]).cuda()
+    ctx.set_heightmap(pyr, None, sc["coarse"], sc["levels"], sc["max_height"])
+    W, H = 640, 363  # ragged last tile
+    cams = ol.cameras_for(sc, 3)
+    shared = hd.SharedFrames(ctx, len(cams), H, W, root=0)
+    if rank == 0:
+        shared.tensor.fill_(7)
+    torch.cuda.synchronize()
+    dist.barrier()
+    tf, ts = hd.tiles_for_rank(rank, world)
+    ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], shadows=True, tile_first=tf, tile_stride=ts, full_frame_output=True), out=shared.tensor)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        whole, _ = ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], shadows=True))
+        torch.cuda.synchronize()
+        assert torch.equal(whole, shared.tensor), "frames assembled over NVLink differ from a single-GPU render"
+    shared.close()
     dist.barrier()
     if rank == 0:
         print("rx_worker: ok", flush=True)

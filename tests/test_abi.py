@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.Color) == 3
     assert C.sizeof(_abi.Camera) == 36
     assert C.sizeof(_abi.Hit) == 16
-    assert C.sizeof(_abi.TraceOpts) == 36
+    assert C.sizeof(_abi.TraceOpts) == 40
     assert C.sizeof(_abi.LasTransform) == 96
 
 
@@ -45,7 +45,7 @@ def test_host_only_entry_points():
     from hmrt import _abi
 
     lib = _abi.load()
-    assert lib.hmrt_version() == 100
+    assert lib.hmrt_version() == 200
     res = (C.c_int * 8)()
     idx = (C.c_int64 * 8)()
     total = C.c_int64()
@@ -60,7 +60,7 @@ def test_host_only_entry_points():
     assert b"argument" in lib.hmrt_error_string(_abi.E_ARG)
     o = _abi.TraceOpts()
     lib.hmrt_trace_opts_default(C.byref(o), 12.5)
-    assert o.max_height == 12.5 and o.tile_stride == 1 and o.shadows == 0
+    assert o.max_height == 12.5 and o.tile_stride == 1 and o.shadows == 0 and o.full_frame_output == 0
 
 
 def test_no_device_means_loud_failure():

@@ -127,3 +127,28 @@ def test_largest_configuration_32768(cuda_ctx):
         ergb, ehits = ol.cpu_trace(ol.oracle().hmrt_oracle_trace, host, None, coarse, levels, W, H, cam, opts, rows=(r0_, r1_))
         ol.assert_same_trace((whole[0][r0_:r1_], hits[0][r0_:r1_]), (ergb[r0_:r1_], ehits[r0_:r1_]), f"32768 rows {r0_}")
     assert (hits[0]["flags"] & 1).mean() > 0.3
+
+
+def test_full_frame_output_layout(cuda_ctx):
+    """hmrt_trace_opts.full_frame_output: tile-sharded calls store their tiles at their place in ONE whole-frame buffer
+    (what the ranks of a multi-GPU render do into rank 0's frame); together they reproduce the unsharded call, rows of
+    other shards are never touched."""
+    import gpulib
+    import hmrt
+
+    sc = ol.scene("r512_l4", seed=9)
+    gpulib.upload_scene(cuda_ctx, sc)
+    W, H = 200, 83  # ragged: 11 tiles, the last one 3 rows; W % 16 != 0 -> byte stores
+    cams = ol.cameras_for(sc, 2)
+    whole, _ = cuda_ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], shadows=True))
+    buf = torch.full((2, H, W, 3), 9, dtype=torch.uint8, device="cuda")
+    for r in (2, 0):
+        cuda_ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], shadows=True, tile_first=r, tile_stride=3, full_frame_output=True), out=buf)
+    torch.cuda.synchronize()
+    rows_1 = [y for t in range(1, 11, 3) for y in range(t * 8, min(H, t * 8 + 8))]
+    assert (buf[:, rows_1] == 9).all(), "rows of the missing shard were written"
+    cuda_ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], shadows=True, tile_first=1, tile_stride=3, full_frame_output=True), out=buf)
+    torch.cuda.synchronize()
+    assert torch.equal(buf, whole)
+    with pytest.raises(hmrt.HmrtError):
+        cuda_ctx.trace_host(W, H, cams, hmrt.trace_opts(sc["max_height"], full_frame_output=True), np.zeros((2, H, W, 3), np.uint8))
