@@ -447,6 +447,9 @@ def _run_gpu_arm(args):
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
     ctx.set_heightmap(pyr, None, COARSE, LEVELS, mh)
+    if args.l2_persist:
+        lvl, ratio = args.l2_persist.split(":")
+        ctx.set_l2_persist(int(lvl), float(ratio))
 
     tile_first, tile_stride = hd.tiles_for_rank(rank, world)
     opts = hmrt.trace_opts(mh, tile_first=tile_first, tile_stride=tile_stride)
@@ -662,6 +665,7 @@ def _run_gpu_arm(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wu,
             "ms_per_step": ms / steps_timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": CONFIG, "terrain_checksum": checksum,
+            "l2_persist_experiment": args.l2_persist or None,
             "arm": f"row tiles of 8 rows interleaved over {world} GPU(s); pyramid replicated by one NCCL broadcast ({bcast_ms} ms); steps alternate between two streams",
             "timed_region": {"steps_timed": steps_timed, "repeats_of_the_k_steps": repeats, "seconds": ms * 1e-3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
@@ -687,6 +691,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the second pose family and the tolerance-mode measurement")
     ap.add_argument("--no-raster", action="store_true", help="skip the rasterisation sub-record")
     ap.add_argument("--raster-points", type=int, default=RASTER_POINTS)
+    ap.add_argument("--l2-persist", default="", help="experiment: LEVEL:HIT_RATIO persisting-L2 window over the pyramid levels >= LEVEL")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

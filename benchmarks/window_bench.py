@@ -30,6 +30,8 @@ def main():
     res, idx, total = hmrt.pyramid_layout(coarse, levels)
     r0 = res[0]
     ctx = hmrt.Context(0)
+    variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
+    ctx.set_window_variant(variant)
     g = torch.Generator(device="cuda").manual_seed(3)
     secs = [[torch.rand(total, device="cuda", generator=g) * 90 for _ in range(2)] for _ in range(2)]
     cols = [[torch.randint(0, 256, (r0, r0, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)] for _ in range(2)]
@@ -70,6 +72,7 @@ def main():
     t_upload = (time.perf_counter() - t0) / 3
     line = {
         "workload": f"window of a {r0}^2-cell section grid (coarse {coarse}, {levels} levels): {total * 4 / 1e6:.1f} MB pyramid + {r0 * r0 * 3 / 1e6:.1f} MB colours per frame",
+        "formulation": "TMA bulk copies (cp.async.bulk), one launch" if variant == 0 else "per-thread 128-bit gather, two launches",
         "compose_window_ms": ms, "algorithmic_GBps": bytes_rw / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peak,
         "roofline_frac": bytes_rw / (ms * 1e-3) / 1e9 / peak,
         "reference_flow_ms": {"host_compose_1_core": 1e3 * t_compose, "upload_pageable_h2d": 1e3 * t_upload, "total": 1e3 * (t_compose + t_upload)},

@@ -68,6 +68,7 @@ int hmrt_create(int device, hmrt_ctx** out) {
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->probe_verdict = -1;
+  c->l2_first_level = -1;
   cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete c;
@@ -171,6 +172,29 @@ int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant) {
 }
 
 int64_t hmrt_launch_count(const hmrt_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int hmrt_set_window_variant(hmrt_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;
+  ctx->window_variant = variant;
+  return 0;
+}
+
+int hmrt_set_l2_persist(hmrt_ctx* ctx, int first_level, float hit_ratio) {
+  if (!ctx || first_level > HMRT_MAX_LEVELS || !(hit_ratio >= 0.0f && hit_ratio <= 1.0f)) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  if (first_level < 1) {
+    ctx->l2_first_level = -1;
+    HMRT_CUDA(cudaCtxResetPersistingL2Cache());
+    return 0;
+  }
+  int max_persist = 0;
+  HMRT_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
+  if (max_persist <= 0) return HMRT_E_STATE;
+  HMRT_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+  ctx->l2_first_level = first_level;
+  ctx->l2_hit_ratio = hit_ratio;
+  return 0;
+}
 
 int hmrt_ipc_alloc(hmrt_ctx* ctx, size_t bytes, void** d_ptr, void* handle64) {
   if (!ctx || !d_ptr || !handle64 || bytes == 0) return HMRT_E_ARG;

@@ -39,6 +39,9 @@ struct hmrt_ctx {
   int scratch_cap;
   int call_set;       /* scratch / frame-constant set of the latest trace call (round robin over kCallSets) */
   unsigned long long* d_stats; /* counters of the instrumented kernels (hmrt_trace_stats) */
+  int window_variant; /* 0 = TMA bulk-copy gather where the planes qualify, 1 = per-thread 128-bit gather (hmrt_set_window_variant) */
+  int l2_first_level; /* experiment (hmrt_set_l2_persist): levels >= this get a persisting-L2 access policy window; -1 = off */
+  float l2_hit_ratio;
   int ctas_per_sm[16]; /* resident CTAs per SM of each trace kernel instantiation (0 = not queried yet) */
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;

@@ -455,7 +455,31 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
   p.bulk_chunks = (uint32_t)(p.total_chunks - tail_chunks);
   p.tail_tiles = (uint32_t)(tail_chunks * 4ull);
   void* args[] = {&p};
-  HMRT_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
+  if (ctx->l2_first_level >= 1 && ctx->l2_first_level < ctx->grid.levels) {
+    /* experiment (hmrt_set_l2_persist): the levels >= l2_first_level -- the front of the pyramid, coarsest first -- are
+     * fetched with the persisting property, everything else of the window with the streaming one */
+    int max_window = 0;
+    HMRT_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+    size_t bytes = (size_t)level_offset(ctx->grid, ctx->l2_first_level - 1) * sizeof(float);
+    if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeAccessPolicyWindow;
+    attr.val.accessPolicyWindow.base_ptr = const_cast<float*>(ctx->grid.pyramid);
+    attr.val.accessPolicyWindow.num_bytes = bytes;
+    attr.val.accessPolicyWindow.hitRatio = ctx->l2_hit_ratio;
+    attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    HMRT_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  } else {
+    HMRT_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream));
+  }
   HMRT_LAUNCHED(ctx);
   return 0;
 }

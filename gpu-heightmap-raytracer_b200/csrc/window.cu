@@ -85,6 +85,133 @@ __global__ void __launch_bounds__(256) compose_colors_kernel(const __grid_consta
   }
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * The same gather as ONE launch of TMA bulk copies.  A window row is, per level, at most two contiguous runs of a section
+ * row (the x wrap): a 2-D tile move with no arithmetic at all, so no thread needs to touch the data.  Every CTA is a single
+ * warp whose first lane drives a ring of kWinStages x 16 KB shared-memory stages: cp.async.bulk global -> shared
+ * (completion on the stage's mbarrier), then cp.async.bulk shared -> global (bulk groups); loads of the next stages are in
+ * flight while a stage is written out.  Planes = the pyramid levels + the colour map, one launch for all of them (the two
+ * launches of the per-thread formulation above left a gap between them).  Planes whose rows / shifts are not multiples of
+ * 16 bytes (the two coarsest levels, odd resolutions) are copied by the warp's lanes directly.
+ */
+constexpr int kWinStages = 7; /* 7 x 16 KB per CTA, two CTAs per SM: up to 12 loads in flight per SM */
+constexpr uint32_t kWinPiece = 16384;
+constexpr int kWinMaxPlanes = HMRT_MAX_LEVELS + 1;
+
+struct WinPlane {
+  const uint8_t* src[2][2];
+  uint8_t* dst;
+  uint32_t row_bytes, rows, shift_bytes, cy, pieces_per_row, tma_ok;
+  uint32_t job_end; /* exclusive prefix end of this plane's jobs */
+};
+struct WinTmaParams {
+  WinPlane plane[kWinMaxPlanes];
+  int n_planes;
+  uint32_t total_jobs;
+};
+
+__device__ __forceinline__ void win_mbar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void win_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void win_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void win_load(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void win_store(void* dst, uint32_t src_s, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(bytes) : "memory");
+}
+
+struct WinJob {
+  const uint8_t *a, *b; /* up to two source runs */
+  uint8_t* dst;
+  uint32_t len_a, len_b, tma_ok;
+};
+
+__device__ __forceinline__ WinJob win_job(const WinTmaParams& p, uint32_t j) {
+  int l = 0;
+  while (j >= p.plane[l].job_end) ++l;
+  const WinPlane& pl = p.plane[l];
+  const uint32_t local = j - (l ? p.plane[l - 1].job_end : 0u);
+  const uint32_t y = local / pl.pieces_per_row, piece = local - y * pl.pieces_per_row;
+  const uint32_t b0 = piece * kWinPiece;
+  const uint32_t len = min(kWinPiece, pl.row_bytes - b0);
+  const uint32_t sy = y + pl.cy, wy = sy >= pl.rows, yy = wy ? sy - pl.rows : sy;
+  const uint32_t s0 = b0 + pl.shift_bytes;
+  WinJob w;
+  w.dst = pl.dst + (size_t)y * pl.row_bytes + b0;
+  w.tma_ok = pl.tma_ok;
+  if (s0 >= pl.row_bytes) { /* wholly in the right-hand section */
+    w.a = pl.src[1][wy] + (size_t)yy * pl.row_bytes + (s0 - pl.row_bytes);
+    w.len_a = len, w.b = nullptr, w.len_b = 0;
+  } else {
+    w.a = pl.src[0][wy] + (size_t)yy * pl.row_bytes + s0;
+    w.len_a = min(len, pl.row_bytes - s0);
+    w.len_b = len - w.len_a;
+    w.b = pl.src[1][wy] + (size_t)yy * pl.row_bytes;
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(32) compose_window_tma_kernel(const __grid_constant__ WinTmaParams p) {
+  extern __shared__ __align__(128) uint8_t win_smem[];
+  __shared__ __align__(8) unsigned long long bars[kWinStages];
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(win_smem);
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    for (int s = 0; s < kWinStages; ++s) win_mbar_init(bar0 + 8 * s);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t n_local = p.total_jobs > blockIdx.x ? (p.total_jobs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  uint32_t phase = 0; /* bit s = parity of the next completion of stage s's mbarrier (only TMA jobs complete a phase) */
+  /* what the write-out of a stage needs, noted when its load is issued (the job arithmetic runs once per job) */
+  __shared__ uint8_t* ring_dst[kWinStages];
+  __shared__ uint32_t ring_len[kWinStages];
+  for (uint32_t k = 0; k < n_local + (kWinStages - 1); ++k) {
+    if (k >= (uint32_t)(kWinStages - 1)) { /* write out job kk */
+      const uint32_t kk = k - (kWinStages - 1);
+      const uint32_t s = kk % kWinStages;
+      if (ring_len[s]) {
+        if (lane == 0) {
+          win_mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+          phase ^= 1u << s;
+          win_store(ring_dst[s], stage0 + s * kWinPiece, ring_len[s]);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else { /* unaligned plane: the lanes copy the piece themselves (small coarse levels, odd resolutions) */
+        const WinJob w = win_job(p, blockIdx.x + kk * gridDim.x);
+        for (uint32_t i = lane; i < w.len_a; i += 32) w.dst[i] = __ldcs(w.a + i);
+        for (uint32_t i = lane; i < w.len_b; i += 32) w.dst[w.len_a + i] = __ldcs(w.b + i);
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory"); /* keeps the group count in step */
+      }
+      __syncwarp();
+    }
+    if (k < n_local) { /* load job k into the stage job k - kWinStages used: its write-out was committed one trip ago */
+      const uint32_t s = k % kWinStages;
+      if (lane == 0) {
+        const WinJob w = win_job(p, blockIdx.x + k * gridDim.x);
+        ring_len[s] = w.tma_ok ? w.len_a + w.len_b : 0u;
+        ring_dst[s] = w.dst;
+        if (w.tma_ok) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          win_mbar_expect(bar0 + 8 * s, w.len_a + w.len_b);
+          win_load(stage0 + s * kWinPiece, w.a, w.len_a, bar0 + 8 * s);
+          if (w.len_b) win_load(stage0 + s * kWinPiece + w.len_a, w.b, w.len_b, bar0 + 8 * s);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace hmrt
 
 extern "C" {
@@ -160,6 +287,56 @@ int hmrt_compose_window(hmrt_ctx* ctx, const hmrt_window_sections* sections, int
   if (quads >= (1ull << 32)) return HMRT_E_SHAPE;
   p.total_quads = (uint32_t)quads;
   hmrt::DeviceGuard guard(ctx->device);
+  /* one launch of TMA bulk copies when the big planes qualify (rows and shifts multiples of 16 bytes) */
+  if (p.vec[0] && (!d_window_color_map || p.col_vec) && ctx->window_variant != 1) {
+    hmrt::WinTmaParams t;
+    memset(&t, 0, sizeof(t));
+    uint64_t jobs = 0;
+    int n = 0;
+    for (int l = 0; l < levels; ++l, ++n) {
+      hmrt::WinPlane& pl = t.plane[n];
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) pl.src[a][b] = reinterpret_cast<const uint8_t*>(p.sec[a][b] + p.idx[l]);
+      pl.dst = reinterpret_cast<uint8_t*>(p.out + p.idx[l]);
+      pl.row_bytes = (uint32_t)p.res[l] * 4u;
+      pl.rows = (uint32_t)p.res[l];
+      pl.shift_bytes = p.cx[l] * 4u;
+      pl.cy = p.cy[l];
+      pl.pieces_per_row = (pl.row_bytes + hmrt::kWinPiece - 1) / hmrt::kWinPiece;
+      pl.tma_ok = p.vec[l];
+      jobs += (uint64_t)pl.rows * pl.pieces_per_row;
+      pl.job_end = (uint32_t)jobs;
+    }
+    if (d_window_color_map) {
+      hmrt::WinPlane& pl = t.plane[n++];
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) pl.src[a][b] = p.col[a][b];
+      pl.dst = p.out_col;
+      pl.row_bytes = (uint32_t)p.res[0] * 3u;
+      pl.rows = (uint32_t)p.res[0];
+      pl.shift_bytes = p.cx[0] * 3u;
+      pl.cy = p.cy[0];
+      pl.pieces_per_row = (pl.row_bytes + hmrt::kWinPiece - 1) / hmrt::kWinPiece;
+      pl.tma_ok = 1;
+      jobs += (uint64_t)pl.rows * pl.pieces_per_row;
+      pl.job_end = (uint32_t)jobs;
+    }
+    if (jobs < (1ull << 32)) {
+      t.n_planes = n;
+      t.total_jobs = (uint32_t)jobs;
+      const size_t smem = (size_t)hmrt::kWinStages * hmrt::kWinPiece;
+      static bool configured = false;
+      if (!configured) {
+        HMRT_CUDA(cudaFuncSetAttribute(hmrt::compose_window_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
+      const unsigned cap_tma = (unsigned)ctx->sm_count * 2u; /* 2 x 112 KB of stages per SM */
+      const unsigned grid = jobs < cap_tma ? (unsigned)jobs : cap_tma;
+      hmrt::compose_window_tma_kernel<<<grid, 32, smem, ctx->stream>>>(t);
+      HMRT_LAUNCHED(ctx);
+      return 0;
+    }
+  }
   const unsigned cap = (unsigned)ctx->sm_count * 8u; /* 8 x 256 threads per SM, grid-stride */
   unsigned blocks = (unsigned)((quads + 255) / 256);
   hmrt::compose_window_kernel<<<blocks < cap ? blocks : cap, 256, 0, ctx->stream>>>(p);

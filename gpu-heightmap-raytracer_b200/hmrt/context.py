@@ -143,6 +143,14 @@ class Context:
         2 = tolerance mode (air phase in one closed-form step; meets the BASELINE acceptance bars, not bit-identical)."""
         check(self.lib.hmrt_set_trace_variant(self._h, int(variant)), "hmrt_set_trace_variant")
 
+    def set_window_variant(self, variant: int):
+        """compose_window: 0 = TMA bulk-copy gather (default), 1 = per-thread 128-bit gather; identical results."""
+        check(self.lib.hmrt_set_window_variant(self._h, int(variant)), "hmrt_set_window_variant")
+
+    def set_l2_persist(self, first_level: int, hit_ratio: float = 1.0):
+        """Experiment: persisting-L2 access policy window over the pyramid levels >= first_level (0 / negative = off)."""
+        check(self.lib.hmrt_set_l2_persist(self._h, int(first_level), float(hit_ratio)), "hmrt_set_l2_persist")
+
     def trace_stats(self, reset: bool = True):
         """{rays, iterations, air_iterations} accumulated by the instrumented kernels (trace(..., hits=...)) since the last reset."""
         out = (C.c_uint64 * 4)()

@@ -319,6 +319,17 @@ int hmrt_rx_bands(const hmrt_rx* rx, int* rows);
  *     no default path and no reported number uses it.  Grids whose coarse_res is not a power of two fall back to variant 0. */
 int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant);
 
+/* hmrt_compose_window formulation: 0 (default) = one launch of TMA bulk copies (cp.async.bulk through shared-memory stages,
+ * no per-thread data movement) wherever rows and shifts are multiples of 16 bytes, 1 = the per-thread 128-bit gather.
+ * Identical results. */
+int hmrt_set_window_variant(hmrt_ctx* ctx, int variant);
+
+/* Experiment ("L2 residency"): fetch the pyramid levels >= first_level with a persisting-L2 access
+ * policy window (cudaAccessPropertyPersisting for `hit_ratio` of the window, streaming for the rest) on every trace launch;
+ * first_level < 1 switches it off and resets the persisting lines.  Measured neutral-to-negative on B200 (126 MB of L2 keep
+ * the coarse levels resident by themselves), hence off by default. */
+int hmrt_set_l2_persist(hmrt_ctx* ctx, int first_level, float hit_ratio);
+
 /* Counters of the instrumented kernels (calls with d_hits != NULL) since the last reset: out[0] = rays, out[1] = loop
  * iterations (== height fetches of the reference algorithm, CudaKernel.cu:153-176; the S of SURVEY.md section 8(d)),
  * out[2] = the share of them taken in the production walk's air phase (arithmetic only, no height fetch), out[3] = 0.

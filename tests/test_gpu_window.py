@@ -39,8 +39,16 @@ def _compose_gpu(ctx, pyr, col, coarse, levels, cx, cy, with_colors):
     return out.cpu().numpy(), (out_c.cpu().numpy() if with_colors else None)
 
 
-@pytest.mark.parametrize("coarse,levels", [(8, 4), (4, 1), (3, 3), (5, 2), (16, 6), (2, 8)])
-def test_compose_window_equals_oracle(cuda_ctx, coarse, levels):
+@pytest.fixture(params=[0, 1], ids=["tma", "per-thread"])
+def window_variant(request, cuda_ctx):
+    """Both formulations of hmrt_compose_window: TMA bulk copies (default) and the per-thread 128-bit gather."""
+    cuda_ctx.set_window_variant(request.param)
+    yield request.param
+    cuda_ctx.set_window_variant(0)
+
+
+@pytest.mark.parametrize("coarse,levels", [(8, 4), (4, 1), (3, 3), (5, 2), (16, 6), (2, 8), (64, 7)])
+def test_compose_window_equals_oracle(cuda_ctx, window_variant, coarse, levels):
     res, idx, total, pyr, col = _host_sections(coarse, levels, seed=100 + coarse + levels)
     cells = {(0, 0), (0, coarse - 1), (coarse - 1, 0), (coarse // 2, coarse // 3), (coarse - 1, coarse - 1), (1 % coarse, 1 % coarse)}
     for cx, cy in sorted(cells):
@@ -119,7 +127,7 @@ def test_reference_frame_flow_place_compose_trace(cuda_ctx):
         assert (hits[0]["flags"] & 1).mean() > 0.5
 
 
-def test_compose_window_default_size_bandwidth(cuda_ctx):
+def test_compose_window_default_size_bandwidth(cuda_ctx, window_variant):
     """The reference's default window (coarse 32, 8 levels: 4096^2 finest, 89.5 MB of floats + 50.3 MB of colours):
     bit-exact against the oracle and, as a sanity bound, faster than 1 ms (the reference uploads it over PCIe every frame)."""
     coarse, levels = 32, 8
