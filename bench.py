@@ -536,7 +536,8 @@ def _run_gpu_arm(args):
         e2e_s = float(t.item())
     e2e = {"value": rays_per_step * K * e2e_repeats / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 36,
            "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / (K * e2e_repeats), "steps_timed": K * e2e_repeats,
-           "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory, copy of frame f overlapped with the traversal of frame f+1; heightmap resident"}
+           "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory; "
+                   "one persistent launch per step, every quarter-frame row segment is copied the moment its last tile is stored (stream memory operation on the copy stream); heightmap resident"}
 
     # ---- frame assembly on the multi-GPU path (the reference delivers ONE complete frame per call, main.cpp:675-703):
     # every rank stores its row tiles straight into rank 0's frames over NVLink from inside the traversal kernel

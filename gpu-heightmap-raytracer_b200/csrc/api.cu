@@ -86,6 +86,7 @@ int hmrt_destroy(hmrt_ctx* ctx) {
   if (ctx->d_fb) cudaFree(ctx->d_fb);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->d_seg_done) cudaFree(ctx->d_seg_done);
   if (ctx->d_ws) cudaFree(ctx->d_ws);
   if (ctx->d_probe) cudaFree(ctx->d_probe);
   if (ctx->copy_stream) {
@@ -172,6 +173,12 @@ int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant) {
 }
 
 int64_t hmrt_launch_count(const hmrt_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int hmrt_set_host_variant(hmrt_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 2) return HMRT_E_ARG;
+  ctx->host_variant = variant;
+  return 0;
+}
 
 int hmrt_set_window_variant(hmrt_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;

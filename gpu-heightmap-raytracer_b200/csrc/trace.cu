@@ -14,6 +14,7 @@
  * coalesced 128-bit stores (byte stores when W % 16 != 0 or on ragged edges).  Many frames
  * (a fly-through, a batch of camera poses) run in ONE launch.
  */
+#include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -43,6 +44,12 @@ struct TraceScratch {
   uint32_t pad;
 };
 
+constexpr int kSegments = 4; /* row segments per frame whose completion is signalled separately */
+struct SegDone {
+  uint32_t units; /* 8 x 4 tiles of the segment stored so far */
+  uint32_t flag;  /* 1 once all of them are (polled by cuStreamWaitValue32 on the copy stream) */
+};
+
 struct TraceParams {
   Grid grid;
   Shading shading;
@@ -64,6 +71,10 @@ struct TraceParams {
   uint32_t chunks_per_frame;       /* local row tiles * 2 * chunks_x */
   uint32_t total_chunks;           /* frames * chunks_per_frame (< 2^31: larger calls are split by the launcher) */
   unsigned long long* stats;       /* instrumented kernels only: {rays, loop iterations, air-phase iterations} accumulated */
+  /* hmrt_trace_host: completion tracking per (frame, row segment) so that the device->host copy of a segment can start the
+   * moment its last tile is stored, while the same launch is still tracing the rest (null: no tracking) */
+  SegDone* seg_done;               /* [frames * kSegments] */
+  uint32_t strips_per_frame;       /* chunks_per_frame / chunks_x */
   /* up to kInlineFrames per-frame constants ride in the kernel parameters: no host->device copy in front
    * of the launch (a 16-frame call spent ~27 us of device timeline on that copy) */
   alignas(16) FrameConsts frame_inline[kInlineFrames];
@@ -132,7 +143,7 @@ enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2, kWalkJumpPow2 
 
 /* One unit of work of a warp: the tiles [k_first, k_last) of chunk `chunk` (all four in the bulk phase -> 128-bit
  * stores; a single one in the tail phase -> 8-byte stores). */
-template <bool HITS, int WALK, bool TAIL>
+template <bool HITS, int WALK, bool TAIL, bool NOTIFY>
 __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, float hmax, FrameConsts* frame_slot,
                                            uint8_t (*stage)[kStageRow], uint32_t chunk, int k_first, int k_last) {
   const int lane = threadIdx.x & 31;
@@ -227,6 +238,22 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
     }
   }
   __syncwarp(); /* the stage slice is reused by the next unit */
+  if (NOTIFY) {
+    if (lane == 0) {
+      /* everything is recomputed from the chunk number: nothing extra stays live across the walk */
+      const uint32_t frame_n = chunk / p.chunks_per_frame;
+      const uint32_t strip_n = p.strips_per_frame - 1u - (chunk - frame_n * p.chunks_per_frame) / p.chunks_x;
+      const uint32_t seg = strip_n * (uint32_t)kSegments / p.strips_per_frame;
+      const uint32_t s_lo = (seg * p.strips_per_frame + kSegments - 1) / kSegments, s_hi = ((seg + 1) * p.strips_per_frame + kSegments - 1) / kSegments;
+      const uint32_t want = (s_hi - s_lo) * p.chunks_x * 4u, mine = (uint32_t)(k_last - k_first);
+      SegDone* sd = p.seg_done + frame_n * kSegments + seg;
+      __threadfence(); /* the tile's stores (ordered before this lane by the __syncwarp) before the count */
+      if (atomicAdd(&sd->units, mine) + mine == want) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(&sd->flag) = 1u;
+      }
+    }
+  }
 }
 
 /*
@@ -238,11 +265,12 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
  * tile's time of each other -- that matters for single-frame launches (interactive use, the per-frame
  * launches of hmrt_trace_host, 1/8 frames on 8 GPUs).  TAILED = false compiles the tail out: for launches
  * with hundreds of chunks per warp the tail is irrelevant and the leaner code is ~1.5 % faster (measured).
+ * NOTIFY (hmrt_trace_host): every unit reports to its (frame, row segment) counter, see SegDone.
  */
 #ifndef HMRT_MIN_CTAS
 #define HMRT_MIN_CTAS (TAILED ? 5 : 0)
 #endif
-template <bool HITS, int WALK, bool TAILED>
+template <bool HITS, int WALK, bool TAILED, bool NOTIFY = false>
 __global__ void __launch_bounds__(kThreads, HMRT_MIN_CTAS) trace_persistent_kernel(const __grid_constant__ TraceParams p) {
   __shared__ __align__(16) uint8_t stage[kWarps][kChunkH][kStageRow];
   __shared__ LevelEntry level_tab[HMRT_MAX_LEVELS];
@@ -263,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, HMRT_MIN_CTAS) trace_persistent_kern
     if (lane == 0) c = atomicAdd(p.next_chunk, 1u);
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c >= p.bulk_chunks) break;
-    trace_unit<HITS, WALK, false>(p, tab, hmax, &frame_s[warp], stage[warp], c, 0, 4);
+    trace_unit<HITS, WALK, false, NOTIFY>(p, tab, hmax, &frame_s[warp], stage[warp], c, 0, 4);
   }
   if (TAILED) {
     for (;;) { /* tail */
@@ -272,15 +300,24 @@ __global__ void __launch_bounds__(kThreads, HMRT_MIN_CTAS) trace_persistent_kern
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= p.tail_tiles) break;
       const int k = (int)(t & 3u);
-      trace_unit<HITS, WALK, true>(p, tab, hmax, &frame_s[warp], stage[warp], p.bulk_chunks + (t >> 2), k, k + 1);
+      trace_unit<HITS, WALK, true, NOTIFY>(p, tab, hmax, &frame_s[warp], stage[warp], p.bulk_chunks + (t >> 2), k, k + 1);
     }
   }
 }
 
-static const void* pick_kernel(bool hits, int walk, bool tailed) {
+static const void* pick_kernel(bool hits, int walk, bool tailed, bool notify) {
 #define HMRT_PICK(HITS_, WALK_)                                                                         \
   return tailed ? reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, true>)           \
                 : reinterpret_cast<const void*>(&trace_persistent_kernel<HITS_, WALK_, false>)
+#define HMRT_PICK_NOTIFY(WALK_)                                                                         \
+  return tailed ? reinterpret_cast<const void*>(&trace_persistent_kernel<false, WALK_, true, true>)     \
+                : reinterpret_cast<const void*>(&trace_persistent_kernel<false, WALK_, false, true>)
+  if (notify) { /* hmrt_trace_host only: no instrumented variant */
+    if (walk == kWalkJumpPow2) HMRT_PICK_NOTIFY(kWalkJumpPow2);
+    if (walk == kWalkFastPow2) HMRT_PICK_NOTIFY(kWalkFastPow2);
+    if (walk == kWalkFast) HMRT_PICK_NOTIFY(kWalkFast);
+    HMRT_PICK_NOTIFY(kWalkReference);
+  }
   if (hits) {
     if (walk == kWalkJumpPow2) HMRT_PICK(true, kWalkJumpPow2);
     if (walk == kWalkFastPow2) HMRT_PICK(true, kWalkFastPow2);
@@ -292,6 +329,7 @@ static const void* pick_kernel(bool hits, int walk, bool tailed) {
   if (walk == kWalkFast) HMRT_PICK(false, kWalkFast);
   HMRT_PICK(false, kWalkReference);
 #undef HMRT_PICK
+#undef HMRT_PICK_NOTIFY
 }
 
 /* Scratch: kCallSets sets of `scratch_cap` slots; a call takes the next set (round robin), its slot 0 also holds the
@@ -360,7 +398,8 @@ static int ensure_frames(hmrt_ctx* ctx, int n) {
 /* `tile_cnt` > 0 (single-frame launches only): render just the local tiles [tile_lo, tile_lo + tile_cnt) of the frame; d_rgb then
  * points at the first row of local tile `tile_lo`. */
 static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
-                        int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits, int tile_lo = 0, int tile_cnt = 0) {
+                        int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits, int tile_lo = 0, int tile_cnt = 0,
+                        SegDone* seg_done = nullptr) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
@@ -436,8 +475,11 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
   /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
   /* tile-granular tail only where it pays: fewer than 64 chunks per resident warp (see the kernel comment) */
   const bool tailed = (unsigned long long)p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
-  const void* fn = pick_kernel(d_hits != nullptr, walk, tailed);
-  const int kslot = (tailed ? 8 : 0) + (d_hits ? 4 : 0) + walk;
+  const bool notify = seg_done != nullptr && !d_hits;
+  const void* fn = pick_kernel(d_hits != nullptr, walk, tailed, notify);
+  const int kslot = (notify ? 16 : 0) + (tailed ? 8 : 0) + (d_hits ? 4 : 0) + walk;
+  p.seg_done = notify ? seg_done : nullptr;
+  p.strips_per_frame = p.chunks_per_frame / p.chunks_x;
   if (ctx->ctas_per_sm[kslot] == 0) {
     int per_sm = 0;
     HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
@@ -513,6 +555,91 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
                             d_hits ? d_hits + (size_t)f0 * frame_px : nullptr);
     if (rc) return rc;
   }
+  return 0;
+}
+
+/* cuStreamWaitValue32 (stream memory operation of the driver API), bound at run time: the runtime API has no equivalent.
+ * "Wait until (int32)(*addr - value) >= 0" (flags = CU_STREAM_WAIT_VALUE_GEQ = 0). */
+typedef int (*stream_wait_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static stream_wait_value32_fn stream_wait_value32() {
+  static stream_wait_value32_fn fn = [] {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return (stream_wait_value32_fn) nullptr;
+    void* f = dlsym(h, "cuStreamWaitValue32_v2");
+    if (!f) f = dlsym(h, "cuStreamWaitValue32");
+    return reinterpret_cast<stream_wait_value32_fn>(f);
+  }();
+  return fn;
+}
+
+/* behind the traversal launch, on the same stream: every segment counts as complete (a safety net: a copy waiting on a
+ * flag can never outlive the launch that should have set it) */
+__global__ void seg_force_kernel(hmrt::SegDone* sd, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&sd[i].flag) = 1u;
+  }
+}
+
+/*
+ * hmrt_trace_host, streaming form: ONE persistent launch over all frames (the same launch shape as hmrt_trace: no per-frame
+ * launch, no per-frame tail) whose units report to per-(frame, row segment) counters; the copy stream waits on each
+ * segment's flag with a stream memory operation and copies the segment's rows the moment its last tile is stored.  The
+ * device->host copies therefore trail the traversal by a quarter of a frame instead of a whole launch.
+ */
+static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames, const hmrt_trace_opts* opts,
+                               uint8_t* h_rgb, size_t frame_bytes, stream_wait_value32_fn wait_value) {
+  const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
+  const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
+  const int local_tiles = opts->tile_first < n_tiles ? (n_tiles - opts->tile_first + stride - 1) / stride : 0;
+  if (local_tiles == 0) return 0;
+  const uint32_t strips = (uint32_t)local_tiles * 2u;
+  const size_t row_bytes = (size_t)W * 3, rows_total = frame_bytes / row_bytes;
+  const int n_seg = n_frames * hmrt::kSegments;
+  if (ctx->seg_cap < n_seg) {
+    if (ctx->d_seg_done) HMRT_CUDA(cudaFree(ctx->d_seg_done));
+    ctx->d_seg_done = nullptr;
+    ctx->seg_cap = 0;
+    HMRT_CUDA(cudaMalloc(&ctx->d_seg_done, sizeof(hmrt::SegDone) * (size_t)n_seg));
+    ctx->seg_cap = n_seg;
+  }
+  hmrt::SegDone* sd = static_cast<hmrt::SegDone*>(ctx->d_seg_done);
+  const int per = frames_per_launch(W, H);
+  const int n_launches = (n_frames + per - 1) / per;
+  int base = 0;
+  int rc = hmrt::prepare_trace(ctx, n_launches, &base);
+  if (rc) return rc;
+  HMRT_CUDA(cudaMemsetAsync(sd, 0, sizeof(hmrt::SegDone) * (size_t)n_seg, ctx->stream));
+  HMRT_CUDA(cudaEventRecord(ctx->prep_event, ctx->stream));
+  HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->prep_event, 0)); /* the flags are zero before anybody polls them */
+  for (int l = 0; l < n_launches; ++l) {
+    const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
+    rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0,
+                            sd + (size_t)f0 * hmrt::kSegments);
+    if (rc) break;
+  }
+  /* the safety net goes in even when a launch failed: the waits below must always be released */
+  seg_force_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->stream>>>(sd, n_seg);
+  if (rc == 0) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    ctx->launches++;
+  }
+  if (rc) return rc;
+  for (int f = 0; f < n_frames; ++f)
+    for (int seg = hmrt::kSegments - 1; seg >= 0; --seg) { /* rows are traced from the top of the frame down */
+      const uint32_t s_lo = ((uint32_t)seg * strips + hmrt::kSegments - 1) / hmrt::kSegments,
+                     s_hi = (((uint32_t)seg + 1u) * strips + hmrt::kSegments - 1) / hmrt::kSegments;
+      if (s_hi <= s_lo) continue;
+      const size_t r0 = (size_t)s_lo * 4, r1 = (size_t)s_hi * 4 < rows_total ? (size_t)s_hi * 4 : rows_total;
+      if (r1 <= r0) continue;
+      const unsigned long long flag = reinterpret_cast<unsigned long long>(&sd[(size_t)f * hmrt::kSegments + seg].flag);
+      const int drc = wait_value(ctx->copy_stream, flag, 1u, 0u);
+      if (drc != 0) return 999; /* cudaErrorUnknown: the driver refused the stream memory operation */
+      const size_t off = (size_t)f * frame_bytes + r0 * row_bytes;
+      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, ctx->d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
   return 0;
 }
 
@@ -606,13 +733,24 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
     }
     HMRT_CUDA(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
   }
-  rc = trace_host_enqueue(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes);
+  /* Schedules (measured on B200, 4K frames, profiles/raw_r02/trace_host_variants.txt): batches of frames are bound by the
+   * device->host link (398 MB per 16-frame step at ~45 GB/s > the 8 ms of traversal), where the per-group schedule is as
+   * good as it gets and the 64 stream operations of the streamed one cost 4 %; a SINGLE frame is latency-bound, where
+   * releasing each quarter frame as it completes wins 6 % (0.90 vs 0.96 ms).  Variant 0 picks accordingly. */
+  const bool streamed = ctx->host_variant == 2 || (ctx->host_variant == 0 && n_frames == 1);
+  stream_wait_value32_fn wait_value = streamed ? stream_wait_value32() : nullptr;
+  if (wait_value)
+    rc = trace_host_streamed(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes, wait_value);
+  else
+    rc = trace_host_enqueue(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes);
+  cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
   /* one exit: whatever was enqueued -- kernels writing d_fb, copies into h_rgb -- has finished when the caller gets
    * control back, also on the error paths */
   cudaError_t e = cudaStreamSynchronize(ctx->frame_stream[0]);
   cudaError_t e1 = cudaStreamSynchronize(ctx->frame_stream[1]);
   cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
   if (rc) return rc;
+  if (e0 != cudaSuccess) return (int)e0;
   if (e != cudaSuccess) return (int)e;
   if (e1 != cudaSuccess) return (int)e1;
   return (int)e2;

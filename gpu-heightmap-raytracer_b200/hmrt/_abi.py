@@ -113,6 +113,7 @@ PROTOTYPES = {
     "hmrt_rx_status": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hmrt_rx_bands": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "hmrt_set_trace_variant": (C.c_int, [_P, C.c_int]),
+    "hmrt_set_host_variant": (C.c_int, [_P, C.c_int]),
     "hmrt_set_window_variant": (C.c_int, [_P, C.c_int]),
     "hmrt_set_l2_persist": (C.c_int, [_P, C.c_int, C.c_float]),
     "hmrt_trace_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),

@@ -143,6 +143,10 @@ class Context:
         2 = tolerance mode (air phase in one closed-form step; meets the BASELINE acceptance bars, not bit-identical)."""
         check(self.lib.hmrt_set_trace_variant(self._h, int(variant)), "hmrt_set_trace_variant")
 
+    def set_host_variant(self, variant: int):
+        """trace_host: 0 = auto (default), 1 = one launch per frame group, 2 = streamed (per-segment copies); identical results."""
+        check(self.lib.hmrt_set_host_variant(self._h, int(variant)), "hmrt_set_host_variant")
+
     def set_window_variant(self, variant: int):
         """compose_window: 0 = TMA bulk-copy gather (default), 1 = per-thread 128-bit gather; identical results."""
         check(self.lib.hmrt_set_window_variant(self._h, int(variant)), "hmrt_set_window_variant")

@@ -319,6 +319,14 @@ int hmrt_rx_bands(const hmrt_rx* rx, int* rows);
  *     no default path and no reported number uses it.  Grids whose coarse_res is not a power of two fall back to variant 0. */
 int hmrt_set_trace_variant(hmrt_ctx* ctx, int variant);
 
+/* hmrt_trace_host schedule.  1 = one launch per group of frames (>= 4 M rays), each followed by its device->host copy on a
+ * copy stream, the last single-frame launch cut into four tile ranges.  2 = streamed: ONE persistent launch over all frames
+ * whose quarter-frame row segments signal their completion; the copy of a segment starts the moment its last tile is stored
+ * (cuStreamWaitValue32 on the copy stream; falls back to 1 when the driver entry point is missing).  0 (default) = streamed
+ * for single-frame calls (latency-bound: -6 %), per-group for batches (bound by the device->host link either way).
+ * Identical results. */
+int hmrt_set_host_variant(hmrt_ctx* ctx, int variant);
+
 /* hmrt_compose_window formulation: 0 (default) = one launch of TMA bulk copies (cp.async.bulk through shared-memory stages,
  * no per-thread data movement) wherever rows and shifts are multiples of 16 bytes, 1 = the per-thread 128-bit gather.
  * Identical results. */

@@ -130,11 +130,20 @@ def test_trace_host_matches_device_and_reference_call_order(cuda_ctx):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("W,H,n_frames,stride", [(3840, 2160, 1, 1), (3840, 2157, 3, 1), (3840, 2160, 5, 2), (2560, 1083, 2, 1)])
-def test_trace_host_large_frames_split_last_launch(cuda_ctx, W, H, n_frames, stride):
-    """hmrt_trace_host groups frames into launches of >= 4 M rays and cuts the LAST single-frame launch into four tile ranges
-    with their own device->host copies; the host buffer must equal the device rendering of hmrt_trace byte for byte --
-    whole frames, ragged last row tile (H % 8 != 0), row-tile sharding."""
+@pytest.fixture(params=[2, 1, 0], ids=["streamed", "per-group", "auto"])
+def host_variant(request, cuda_ctx):
+    """The schedules of hmrt_trace_host: one launch + per-segment stream waits, one launch per frame group, and the default mix."""
+    cuda_ctx.set_host_variant(request.param)
+    yield request.param
+    cuda_ctx.set_host_variant(0)
+
+
+@pytest.mark.parametrize("W,H,n_frames,stride", [(3840, 2160, 1, 1), (3840, 2157, 3, 1), (3840, 2160, 5, 2), (2560, 1083, 2, 1), (200, 43, 3, 3)])
+def test_trace_host_large_frames_split_last_launch(cuda_ctx, host_variant, W, H, n_frames, stride):
+    """hmrt_trace_host, streamed: one launch whose row segments release their device->host copies as they complete;
+    per-group: launches of >= 4 M rays, the LAST single-frame launch cut into four tile ranges with their own copies.
+    Either way the host buffer must equal the device rendering of hmrt_trace byte for byte -- whole frames, ragged last
+    row tile (H % 8 != 0), row-tile sharding, frames with fewer strips than segments."""
     import gpulib
 
     sc = ol.scene("r1024_l8", seed=3)
@@ -148,7 +157,7 @@ def test_trace_host_large_frames_split_last_launch(cuda_ctx, W, H, n_frames, str
         assert (host.numpy() == dev).all()
 
 
-def test_many_frames_in_one_call_equal_single_frame_calls(cuda_ctx):
+def test_many_frames_in_one_call_equal_single_frame_calls(cuda_ctx, host_variant):
     """More frames than fit in the kernel parameters (48) travel through the device-side frame table; device and host
     output of a 70-frame call must equal 70 single-frame calls."""
     import gpulib
