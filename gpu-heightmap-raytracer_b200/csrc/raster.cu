@@ -214,7 +214,7 @@ int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int rec
   const int tiles_x = (res[0] + (1 << tile_shift) - 1) >> tile_shift;
   const int n_tiles = tiles_x * tiles_x;
   bool binned = false;
-  const bool binnable = !d_color_keys && n_tiles >= 64 && (reinterpret_cast<uintptr_t>(d_records) & 15) == 0 && record_len <= 64;
+  const bool binnable = n_tiles >= 64 && (reinterpret_cast<uintptr_t>(d_records) & 15) == 0 && record_len <= 64;
   if (binnable && ctx->scatter_mode == 2) binned = true; /* forced (tests, benchmarks) */
   if (binnable && ctx->scatter_mode == 0 && n >= (int64_t)1 << 22 && (size_t)res[0] * res[0] * 4 > ((size_t)96 << 20)) {
     /* the probe costs one stream synchronisation: once per input (first_index == 0), later chunks of the same file reuse the verdict */
@@ -237,7 +237,8 @@ int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int rec
     }
     binned = ctx->probe_verdict == 1;
   }
-  if (binned) return hmrt::scatter_binned_single(ctx, d_records, n, record_len, sp, finest);
+  if (binned)
+    return hmrt::scatter_binned_single(ctx, d_records, n, record_len, sp, finest, reinterpret_cast<unsigned long long*>(d_color_keys), first_index);
 
   const int64_t blocks = (n + hmrt::kScatterThreads - 1) / hmrt::kScatterThreads;
   if (blocks > 0x7fffffffLL) return HMRT_E_SHAPE;

@@ -57,19 +57,25 @@ struct RxHeader {
   uint32_t error;            /* 1 = a barrier timed out */
 };
 
+template <bool KEYS> struct PairOf { typedef uint2 type; };
+template <> struct PairOf<true> { typedef uint4 type; };
+
 struct BinParams {
   ScatterParams sp;
   const uint8_t* records;
   int64_t n;
   int record_len;
   int per;                /* records per thread and step: chunk = kBinThreads * per */
-  uint2* pairs;           /* [n_tiles][n_slices][slice_cap] (cell, height bits) */
+  void* pairs;            /* [n_tiles][n_slices][slice_cap] (cell, height bits) pairs, or -- with colour keys -- (cell, height
+                           * bits, key lo, key hi) quads */
   uint32_t* counts;       /* [n_tiles][n_slices] */
   uint32_t slice_cap;
   int tile_shift, tiles_x, n_tiles;
   int* finest;            /* single GPU: overflowing points go straight to the grid; NULL: they are counted in *overflow */
+  unsigned long long* keys; /* colour keys next to `finest` (single GPU, KEYS instantiation) */
   uint32_t* overflow;
   int accumulate;         /* continue the slices of an earlier call of the same rasterisation */
+  int64_t first_index;    /* colour keys: file index of record 0 (main.cpp:223-224: the last writer in file order wins) */
 };
 
 /* ---- mbarrier / TMA bulk copy (sm_90+) -------------------------------------------------------------------------- */
@@ -95,12 +101,24 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                : "memory");
 }
 
+__device__ __forceinline__ void store_pair(uint2* dst, uint32_t cell, uint32_t hb, uint32_t, int64_t) { *dst = make_uint2(cell, hb); }
+__device__ __forceinline__ void store_pair(uint4* dst, uint32_t cell, uint32_t hb, uint32_t rgb, int64_t file_index) {
+  const unsigned long long key = ((unsigned long long)(file_index + 1) << 24) | rgb; /* +1: key 0 means "never written" */
+  *dst = make_uint4(cell, hb, (uint32_t)key, (uint32_t)(key >> 32));
+}
+__device__ __forceinline__ void apply_pair(int* finest, unsigned long long*, const uint2& v) { atomicMax(finest + v.x, (int)v.y); }
+__device__ __forceinline__ void apply_pair(int* finest, unsigned long long* keys, const uint4& v) {
+  atomicMax(keys + v.x, ((unsigned long long)v.w << 32) | v.z); /* main.cpp:223-224 */
+  if (v.y) atomicMax(finest + v.x, (int)v.y);                    /* :227-233 */
+}
+
 /*
  * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][sdest: chunk u32][spair: chunk uint2]
  * [stage 0][stage 1], a stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
  */
-template <int THREADS>
+template <int THREADS, bool KEYS>
 __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__ BinParams p) {
+  typedef typename PairOf<KEYS>::type Pair;
   extern __shared__ __align__(128) uint8_t rx_smem[];
   const int chunk = THREADS * p.per;
   uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + 16); /* entries used in this CTA's slice of each bucket (persistent) */
@@ -108,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
   uint32_t* offs = hist + kMaxTiles;                          /* exclusive prefix of hist */
   uint32_t* dest0 = offs + kMaxTiles;                         /* first destination index of this step's run, or ~0u: slice full */
   uint32_t* sdest = dest0 + kMaxTiles;                        /* [chunk] destination pair index per sorted slot */
-  uint2* spair = reinterpret_cast<uint2*>(sdest + chunk);     /* [chunk] sorted pairs */
+  Pair* spair = reinterpret_cast<Pair*>((reinterpret_cast<uintptr_t>(sdest + chunk) + 15) & ~(uintptr_t)15); /* [chunk] sorted pairs */
   const uint32_t stage_bytes = ((uint32_t)chunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
   uint8_t* stage0 = reinterpret_cast<uint8_t*>(spair + chunk);
   stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
      * the XU pipe: (double)int32 by the 2^52 + 2^31 bias trick (exact), and -- since floor(t) >= 0 <=> t >= 0 and
      * floor(t) < res0 <=> t < res0 for an integer res0 -- the range test on t itself and floor(t) read off the significand of
      * t + 2^23 rounded toward -inf (0 <= t < 2^23). */
-    uint32_t cell[kMaxPer], hb[kMaxPer], slot[kMaxPer];
+    uint32_t cell[kMaxPer], hb[kMaxPer], slot[kMaxPer], rgb[KEYS ? kMaxPer : 1];
     const float r0f = (float)p.sp.res0;
     const bool aligned4 = (p.record_len & 3) == 0;
 #pragma unroll
@@ -197,11 +215,23 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
         const float fZ = div_cell(__double2float_rn(__dsub_rn(gz, p.sp.mn[2])), p.sp.cell[2], p.sp.rcell[2]); /* :202 */
         const float tx = __fsub_rn(fX, p.sp.origin[0]), ty = __fsub_rn(fY, p.sp.origin[1]);                   /* :205-206 */
         const bool inside = tx >= 0.0f && tx < r0f && ty >= 0.0f && ty < r0f;                                 /* :209 */
-        if (inside && ((rh.tail >> 24) & 0x1fu) != 7u && fZ >= 0.0f) {
+        /* the colour is written before the height test (main.cpp:223-224 precede :229): with keys, points below the floor
+         * still travel, carrying +0.0f (a no-op for the height) */
+        if (inside && ((rh.tail >> 24) & 0x1fu) != 7u && (KEYS || fZ >= 0.0f)) {
           const uint32_t cx = __float_as_uint(__fadd_rd(tx, 8388608.0f)) & 0x7fffffu;
           const uint32_t cy = __float_as_uint(__fadd_rd(ty, 8388608.0f)) & 0x7fffffu;
           cell[q] = cx + cy * (uint32_t)p.sp.res0;
-          hb[q] = __float_as_uint(fZ);
+          hb[q] = fZ >= 0.0f ? __float_as_uint(fZ) : 0u;
+          if (KEYS) {
+            rgb[q] = 0;
+            if (p.sp.rgb_off >= 0) { /* three u16, 2-byte aligned in every LAS 1.2 format */
+              uint32_t r16, g16, b16;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r16) : "r"(ra + (uint32_t)p.sp.rgb_off));
+              asm volatile("ld.shared.u16 %0, [%1+2];" : "=r"(g16) : "r"(ra + (uint32_t)p.sp.rgb_off));
+              asm volatile("ld.shared.u16 %0, [%1+4];" : "=r"(b16) : "r"(ra + (uint32_t)p.sp.rgb_off));
+              rgb[q] = (color16(r16) << 16) | (color16(g16) << 8) | color16(b16);
+            }
+          }
           const uint32_t tile = (cy >> p.tile_shift) * (uint32_t)p.tiles_x + (cx >> p.tile_shift);
           slot[q] = (tile << 16) | atomicAdd(&hist[tile], 1u); /* rank < chunk <= 4096 */
         }
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
       if (slot[q] == 0xffffffffu) continue;
       const uint32_t tile = slot[q] >> 16, rank = slot[q] & 0xffffu;
       const uint32_t j = offs[tile] + rank, d0 = dest0[tile];
-      spair[j] = make_uint2(cell[q], hb[q]);
+      store_pair(spair + j, cell[q], hb[q], KEYS ? rgb[q] : 0u, p.first_index + c * chunk + (int64_t)(q * THREADS + (int)threadIdx.x));
       sdest[j] = d0 == 0xffffffffu ? d0 : d0 + rank;
     }
     __syncthreads();
@@ -256,11 +286,11 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
     uint32_t dropped = 0;
     for (uint32_t j = threadIdx.x; j < total; j += THREADS) {
       const uint32_t d = sdest[j];
-      const uint2 v = spair[j];
+      const Pair v = spair[j];
       if (d != 0xffffffffu)
-        p.pairs[d] = v;
+        static_cast<Pair*>(p.pairs)[d] = v;
       else if (p.finest)
-        atomicMax(p.finest + v.x, (int)v.y);
+        apply_pair(p.finest, p.keys, v);
       else
         ++dropped;
     }
@@ -282,8 +312,10 @@ struct ApplyParams {
   uint32_t slices_per_cta;
   int* dst;
   uint32_t cell_base;
+  unsigned long long* keys; /* KEYS instantiation (single GPU): colour keys, indexed like dst */
 };
 
+template <bool KEYS>
 __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_constant__ ApplyParams p) {
   const uint32_t tile = p.tile_first + blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile;
   const uint32_t all = p.world * p.n_slices;
@@ -293,6 +325,21 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
     const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
     const uint8_t* base = p.peer[src_rank];
     const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.n_slices + s);
+    if (KEYS) { /* one 16-byte quad per point */
+      const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
+      for (uint32_t i = threadIdx.x; i < count; i += kBinThreads * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t j = i + (uint32_t)k * kBinThreads;
+          v[k] = j < count ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + (uint32_t)k * kBinThreads < count) apply_pair(dst, p.keys, v[k]);
+      }
+      continue;
+    }
     const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
     const uint4* src4 = reinterpret_cast<const uint4*>(src);
     const uint32_t n4 = count >> 1; /* whole 16-byte pieces */
@@ -375,17 +422,18 @@ struct BinGeometry {
 /* development knobs (benchmarks/raster_probe.py); 0 = the built-in choice */
 static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_apply_slices = 0;
 
-static int bin_geometry(int record_len, BinGeometry& g) {
+static int bin_geometry(int record_len, bool keys, BinGeometry& g) {
   /* 512 threads x 4 records = steps of 2048 points (runs of ~8 pairs per tile): measured best of {256, 512} x {2, 4, 8}
    * (profiles/raw_r02/raster_probe_*.json) */
   g.threads = g_knob_bin_threads ? g_knob_bin_threads : 512;
   g.per = g_knob_bin_per ? g_knob_bin_per : 4;
   if (g.threads * g.per > 4096) g.per = 4096 / g.threads;
-  g.fn = g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512>) : reinterpret_cast<const void*>(&rx_bin_kernel<256>);
+  g.fn = keys ? (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, true>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, true>))
+              : (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, false>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, false>));
   for (;;) {
     g.chunk = g.threads * g.per;
     const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + sizeof(uint2)) + 128 + 2 * stage;
+    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
     if (g.smem <= 220 * 1024 || g.per == 1) break;
     g.per >>= 1; /* long records: smaller steps */
   }
@@ -407,9 +455,11 @@ static int64_t slice_capacity(int64_t points, int n_tiles, int n_slices) {
   return cap < 64 ? 64 : cap;
 }
 
-int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, const ScatterParams& sp, int* finest) {
+int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, const ScatterParams& sp, int* finest,
+                          unsigned long long* keys, int64_t first_index) {
   BinGeometry bg;
-  int rc = bin_geometry(record_len, bg);
+  int rc = bin_geometry(record_len, keys != nullptr, bg);
+  const size_t pair_size = keys ? sizeof(uint4) : sizeof(uint2);
   if (rc) return rc;
   const int tile_shift = binned_tile_shift(sp.res0);
   const int tiles_x = (sp.res0 + (1 << tile_shift) - 1) >> tile_shift;
@@ -424,7 +474,7 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     const int64_t slice_cap = slice_capacity(nb, n_tiles, n_slices);
     if ((unsigned long long)n_tiles * (unsigned long long)n_slices * (unsigned long long)slice_cap >= (1ull << 32)) return HMRT_E_SHAPE;
     const size_t counts_bytes = ((size_t)n_tiles * (size_t)n_slices * sizeof(uint32_t) + 255) & ~(size_t)255;
-    const size_t need = counts_bytes + (size_t)n_tiles * (size_t)n_slices * (size_t)slice_cap * sizeof(uint2);
+    const size_t need = counts_bytes + (size_t)n_tiles * (size_t)n_slices * (size_t)slice_cap * pair_size;
     if (ctx->ws_cap < need) {
       if (ctx->d_ws) HMRT_CUDA(cudaFree(ctx->d_ws));
       ctx->d_ws = nullptr;
@@ -440,7 +490,9 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     bp.record_len = record_len;
     bp.per = bg.per;
     bp.counts = reinterpret_cast<uint32_t*>(ws);
-    bp.pairs = reinterpret_cast<uint2*>(ws + counts_bytes);
+    bp.pairs = ws + counts_bytes;
+    bp.keys = keys;
+    bp.first_index = first_index + first;
     bp.slice_cap = (uint32_t)slice_cap;
     bp.tile_shift = tile_shift;
     bp.tiles_x = tiles_x;
@@ -464,7 +516,11 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     ap.groups_per_tile = (uint32_t)((n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
     ap.dst = finest;
     ap.cell_base = 0;
-    rx_apply_kernel<<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
+    ap.keys = keys;
+    if (keys)
+      rx_apply_kernel<true><<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
+    else
+      rx_apply_kernel<false><<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
     HMRT_LAUNCHED(ctx);
   }
   return 0;
@@ -626,7 +682,7 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   if (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15)) return HMRT_E_ARG;
   hmrt::DeviceGuard guard(rx->ctx->device);
   hmrt::BinGeometry bg;
-  int rc = hmrt::bin_geometry(record_len, bg);
+  int rc = hmrt::bin_geometry(record_len, false, bg);
   if (rc) return rc;
   hmrt::BinParams bp;
   rc = hmrt::fill_scatter_params(xf, rx->res0, bp.sp);
@@ -638,7 +694,9 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   bp.record_len = record_len;
   bp.per = bg.per;
   bp.counts = reinterpret_cast<uint32_t*>(rx->region + rx->counts_off);
-  bp.pairs = reinterpret_cast<uint2*>(rx->region + rx->pairs_off);
+  bp.pairs = rx->region + rx->pairs_off;
+  bp.keys = nullptr;
+  bp.first_index = 0;
   bp.slice_cap = rx->slice_cap;
   bp.tile_shift = rx->tile_shift;
   bp.tiles_x = rx->tiles_x;
@@ -692,7 +750,7 @@ int hmrt_rx_apply(hmrt_rx* rx) {
   ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
   ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
   const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;
-  hmrt::rx_apply_kernel<<<grid, hmrt::kBinThreads, 0, rx->ctx->stream>>>(ap);
+  hmrt::rx_apply_kernel<false><<<grid, hmrt::kBinThreads, 0, rx->ctx->stream>>>(ap);
   HMRT_LAUNCHED(rx->ctx);
   return 0;
 }

@@ -73,6 +73,66 @@ def test_rx_origin_cell_size_and_levels(cuda_ctx):
         assert (got.view(np.uint32) == want.view(np.uint32)).all()
 
 
+def test_non_power_of_two_grid_in_every_scatter_mode(cuda_ctx):
+    """coarse_res 21 (2688^2 cells: 11 x 11 grid tiles of 256 cells, the last ones ragged): direct, forced tile-binned and the
+    exchange path agree with the oracle (the old binned path's shared-memory table grew with the tile count)."""
+    r0, levels = 2688, 8
+    coarse = r0 >> (levels - 1)
+    assert coarse == 21
+    hdr, rec = rl.synthetic_las(900_000, r0, point_format=0, seed=21)
+    want, _ = rl.oracle_rasterise(hdr, rec, coarse, levels, with_colors=False)
+    res, idx, total = ol.pyramid_layout(coarse, levels)
+    d = torch.from_numpy(rec).cuda()
+    xf = hdr.transform()
+    try:
+        for mode in (1, 2):
+            cuda_ctx.set_scatter_mode(mode)
+            pyr = torch.empty(total, dtype=torch.float32, device="cuda")
+            cuda_ctx.clear_section(pyr, coarse, levels)
+            cuda_ctx.scatter_las(d, len(rec), rec.shape[1], 0, xf, pyr, coarse, levels)
+            cuda_ctx.build_mips(pyr, coarse, levels)
+            torch.cuda.synchronize()
+            assert (pyr.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all(), f"scatter mode {mode}"
+    finally:
+        cuda_ctx.set_scatter_mode(0)
+    got, overflow, err = _rx_rasterise(cuda_ctx, hdr, rec, coarse, levels)
+    assert overflow == 0 and err == 0 and (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("fmt,record_len", [(2, None), (3, None), (2, 32)])
+def test_binned_scatter_carries_colour_keys(cuda_ctx, fmt, record_len):
+    """A coloured unordered cloud through the tile-binned path (scatter mode 2): heights AND the colour map -- last writer in
+    FILE order wins (main.cpp:223-224), also for points whose height loses or lies below the floor -- equal the oracle and
+    the direct path, with the input in two chunks (first_index) and a shuffled copy of it."""
+    r0, levels = 2048, 8
+    coarse = r0 >> (levels - 1)
+    res, idx, total = ol.pyramid_layout(coarse, levels)
+    hdr, rec = rl.synthetic_las(600_000, r0, point_format=fmt, seed=40 + fmt, record_len=record_len)
+    want_p, want_c = rl.oracle_rasterise(hdr, rec, coarse, levels)
+    xf = hdr.transform()
+    out = {}
+    try:
+        for mode in (1, 2):
+            cuda_ctx.set_scatter_mode(mode)
+            pyr = torch.empty(total, dtype=torch.float32, device="cuda")
+            keys = torch.empty(r0 * r0, dtype=torch.int64, device="cuda")
+            cmap = torch.empty((r0, r0, 3), dtype=torch.uint8, device="cuda")
+            cuda_ctx.clear_section(pyr, coarse, levels, keys, cmap)
+            half = len(rec) // 2 // 8 * 8  # second chunk 16-byte aligned for every record length used here
+            for a, b in ((0, half), (half, len(rec))):
+                d = torch.from_numpy(np.ascontiguousarray(rec[a:b])).cuda()
+                cuda_ctx.scatter_las(d, b - a, rec.shape[1], fmt, xf, pyr, coarse, levels, first_index=a, color_keys=keys)
+            cuda_ctx.build_mips(pyr, coarse, levels)
+            cuda_ctx.resolve_colors(keys, cmap, r0 * r0)
+            torch.cuda.synchronize()
+            out[mode] = (pyr.cpu().numpy(), cmap.cpu().numpy())
+    finally:
+        cuda_ctx.set_scatter_mode(0)
+    for mode in (1, 2):
+        assert (out[mode][0].view(np.uint32) == want_p.view(np.uint32)).all(), f"heights, mode {mode}"
+        assert (out[mode][1] == want_c).all(), f"colours, mode {mode}"
+
+
 def test_rx_empty_input_and_overflow_report(cuda_ctx):
     r0, levels = 2048, 8
     coarse = r0 >> (levels - 1)

@@ -45,7 +45,7 @@ def test_every_kernel_is_present(sass):
 
 def test_packed_walk_is_not_contracted(sass):
     prod = {n: ins for n, ins in sass.items() if "trace_persistent_kernel" in n and ("ELi1E" in n or "ELi2E" in n)}
-    assert len(prod) == 8  # {hits, no hits} x {pow2, generic} x {tile-granular tail, none}
+    assert len(prod) == 12  # {hits, no hits, no hits + segment notify (hmrt_trace_host)} x {pow2, generic} x {tile-granular tail, none}
     for name, ins in prod.items():
         floor_rm = sum(i.startswith("FFMA2.RM") for i in ins)
         ffma2 = sum(i.startswith("FFMA2 ") for i in ins)
@@ -55,8 +55,8 @@ def test_packed_walk_is_not_contracted(sass):
         assert not any(re.match(r"D(FMA|ADD|MUL)\b", i) for i in ins), f"{name}: fp64 arithmetic on the traced path"
     # the air loop of the production kernel: four steps per trip, no register copies, no constant-bank loads
     for name, ins in prod.items():
-        if "ILb0E" not in name:
-            continue  # the instrumented (hits) variants also count iterations inside the loop
+        if "ILb0E" not in name or name.endswith("Lb1EEEvNS_11TraceParamsE"):
+            continue  # the instrumented (hits) variants also count iterations inside the loop; the notify variants are the host path
         rm = [k for k, i in enumerate(ins) if i.startswith("FFMA2.RM")]
         end = next(k for k in range(rm[3], len(ins)) if "BRA" in ins[k])
         body = [re.sub(r"^@!?U?P\d+\s+", "", i) for i in ins[rm[0]:end + 1]]
