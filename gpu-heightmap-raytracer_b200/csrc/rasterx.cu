@@ -572,6 +572,9 @@ int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int worl
   const int shift = hmrt::binned_tile_shift(res[0]);
   /* bands are whole tile rows and must be whole 128-row mip tiles; the fused mip kernel covers 8 levels */
   if (res[0] % 128 != 0 || shift < 7 || levels > 8 || levels < 2) return HMRT_E_SHAPE;
+  /* the fused gather + mip kernel moves 16-byte pieces of level 0 and 8-byte pieces of level 1: odd coarse resolutions put
+   * those levels at odd float offsets */
+  if (idx[0] % 4 != 0 || idx[1] % 2 != 0) return HMRT_E_SHAPE;
   hmrt::DeviceGuard guard(ctx->device);
   hmrt_rx* rx = new (std::nothrow) hmrt_rx();
   if (!rx) return HMRT_E_NOMEM;

@@ -286,7 +286,7 @@ int hmrt_allreduce_max_heights(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid,
  *     hmrt_rx_status -> overflow must be 0 on every rank (else: rerun with a larger max_points_per_rank or use the all-reduce path)
  *
  * Everything is asynchronous on the context's stream except hmrt_rx_status; the barriers are flag exchanges in peer memory
- * with a ~10 s time-out (reported by hmrt_rx_status, never a hang).  Needs res0 % 128 == 0, res0 >= 2048, 2 <= levels <= 8
+ * with a ~10 s time-out (reported by hmrt_rx_status, never a hang).  Needs res0 % 128 == 0, res0 >= 2048, an even coarse_res, 2 <= levels <= 8
  * (HMRT_E_SHAPE otherwise) and 16-byte aligned records of at most 64 bytes.  world == 1 works without any peer (tests).
  * Colour keys are not carried by this path (use hmrt_scatter_las + hmrt_allreduce_max_heights for coloured clouds).
  */
