@@ -37,6 +37,8 @@ struct hmrt_ctx {
   float init_max_height;
   void* d_scratch;    /* TraceScratch[kCallSets][scratch_cap]: max(top level) key + one work counter per launch of a call */
   int scratch_cap;
+  cudaStream_t last_trace_stream; /* stream of the previous hmrt_trace call: a caller that alternates streams overlaps its calls */
+  bool have_last_trace_stream;
   int call_set;       /* scratch / frame-constant set of the latest trace call (round robin over kCallSets) */
   unsigned long long* d_stats; /* counters of the instrumented kernels (hmrt_trace_stats) */
   void* d_seg_done;   /* SegDone[seg_cap]: per-(frame, row segment) completion of hmrt_trace_host's streaming form */

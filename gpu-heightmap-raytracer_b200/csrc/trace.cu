@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(1024) trace_prep_kernel(const float* __restric
   }
 }
 
+/* development knobs (benchmarks/shard_probe.py): -1 / 0 = the built-in choice */
+static int g_knob_tailed = -1, g_knob_tail_per_warp = 0;
+
 /* WALK: kWalkFast* = production walk (ray_fast.cuh); kWalkReference = operation-by-operation walk
  * (ray_core.cuh), kept as the in-library parity reference (hmrt_set_trace_variant). */
 enum Walk { kWalkReference = 0, kWalkFast = 1, kWalkFastPow2 = 2, kWalkJumpPow2 = 3 /* tolerance mode, see ray_fast.cuh */ };
@@ -399,7 +402,7 @@ static int ensure_frames(hmrt_ctx* ctx, int n) {
  * points at the first row of local tile `tile_lo`. */
 static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
                         int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits, int tile_lo = 0, int tile_cnt = 0,
-                        SegDone* seg_done = nullptr) {
+                        SegDone* seg_done = nullptr, bool overlapped = false) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
@@ -474,7 +477,11 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
                                              : kWalkFastPow2;
   /* persistent grid: SMs x resident CTAs of the chosen instantiation, never more warps than chunks */
   /* tile-granular tail only where it pays: fewer than 64 chunks per resident warp (see the kernel comment) */
-  const bool tailed = (unsigned long long)p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
+  /* ... and only for launches that run alone: when the caller overlaps successive calls (alternating streams, see hmrt_trace)
+   * the next call's head fills the drain, and the lean kernel wins (a 1/8-frame-share step of the benchmark: 1.001 ms
+   * without the tail, 1.049 ms with it, 0.984 ms = one eighth of the whole-frame step; benchmarks/shard_probe.py) */
+  bool tailed = !overlapped && (unsigned long long)p.total_chunks < 64ull * (unsigned long long)ctx->sm_count * 5ull * kWarps;
+  if (g_knob_tailed >= 0) tailed = g_knob_tailed != 0;
   const bool notify = seg_done != nullptr && !d_hits;
   const void* fn = pick_kernel(d_hits != nullptr, walk, tailed, notify);
   const int kslot = (notify ? 16 : 0) + (tailed ? 8 : 0) + (d_hits ? 4 : 0) + walk;
@@ -490,7 +497,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   /* the tail must be long enough to absorb the longest whole chunk claimed just before it (four near-horizon tiles
    * can take ~10x the mean): 8 chunks per resident warp measured best (1: -4 %, everything tile by tile: -5 %) */
-  constexpr unsigned long long tail_per_warp = 8ull;
+  const unsigned long long tail_per_warp = g_knob_tail_per_warp > 0 ? (unsigned long long)g_knob_tail_per_warp : 8ull;
   unsigned long long tail_chunks = (unsigned long long)grid * kWarps * tail_per_warp;
   if (tail_chunks > p.total_chunks) tail_chunks = p.total_chunks;
   if (!tailed) tail_chunks = 0;
@@ -544,6 +551,10 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
   hmrt::DeviceGuard guard(ctx->device);
   const int per = frames_per_launch(W, H);
   const int n_launches = (n_frames + per - 1) / per;
+  /* a caller that switches streams between consecutive calls (HMRT_MAX_CALLS_IN_FLIGHT) is overlapping them */
+  const bool overlapped = ctx->have_last_trace_stream && ctx->last_trace_stream != ctx->stream;
+  ctx->last_trace_stream = ctx->stream;
+  ctx->have_last_trace_stream = true;
   int base = 0;
   rc = hmrt::prepare_trace(ctx, n_launches, &base);
   if (rc) return rc;
@@ -552,7 +563,7 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
   for (int l = 0; l < n_launches; ++l) {
     const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
     rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, d_rgb ? d_rgb + (size_t)f0 * frame_px * 3 : nullptr,
-                            d_hits ? d_hits + (size_t)f0 * frame_px : nullptr);
+                            d_hits ? d_hits + (size_t)f0 * frame_px : nullptr, 0, 0, nullptr, overlapped);
     if (rc) return rc;
   }
   return 0;
@@ -754,6 +765,15 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
   if (e != cudaSuccess) return (int)e;
   if (e1 != cudaSuccess) return (int)e1;
   return (int)e2;
+}
+
+/* Development knobs of the traversal launcher (not part of include/hmrt.h): key 0 = tile-granular tail (-1 auto, 0 off,
+ * 1 on), key 1 = chunks per resident warp handed out tile by tile (0 = built-in 8). */
+int hmrt_debug_trace_knob(int key, int value) {
+  if (key == 0 && value >= -1 && value <= 1) hmrt::g_knob_tailed = value;
+  else if (key == 1 && value >= 0 && value <= 64) hmrt::g_knob_tail_per_warp = value;
+  else return HMRT_E_ARG;
+  return 0;
 }
 
 /* Counters of the INSTRUMENTED kernels (d_hits != NULL) since the last reset: out[0] = rays, out[1] = loop iterations

@@ -143,7 +143,8 @@ void hmrt_trace_opts_default(hmrt_trace_opts* opts, float max_height);
 
 /* Up to HMRT_MAX_CALLS_IN_FLIGHT hmrt_trace calls may be in flight at once when the caller switches streams between them
  * (hmrt_set_stream): every call takes its own set of work counters, so a renderer that double-buffers its frames overlaps
- * the drain of one call with the head of the next.  Calls on ONE stream simply serialise. */
+ * the drain of one call with the head of the next (a call issued on another stream than the previous one is assumed to
+ * overlap with it and takes the launch shape that is best for that).  Calls on ONE stream simply serialise. */
 #define HMRT_MAX_CALLS_IN_FLIGHT 4
 
 /* == CudaSpace::rayTrace (CudaKernel.cuh:49, CudaKernel.cu:291-308) + cuda_setParameters

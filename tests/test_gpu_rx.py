@@ -95,8 +95,14 @@ def test_non_power_of_two_grid_in_every_scatter_mode(cuda_ctx):
             assert (pyr.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all(), f"scatter mode {mode}"
     finally:
         cuda_ctx.set_scatter_mode(0)
-    got, overflow, err = _rx_rasterise(cuda_ctx, hdr, rec, coarse, levels)
-    assert overflow == 0 and err == 0 and (got.view(np.uint32) == want.view(np.uint32)).all()
+    # odd coarse resolution: level 0 starts at an odd float offset -> the exchange path declines, the host falls back
+    rx = C.c_void_p()
+    assert cuda_ctx.lib.hmrt_rx_create(cuda_ctx._h, coarse, levels, 0, 1, 1000, C.byref(rx)) == -3
+    # 20 x 128 = 2560 cells (10 x 10 tiles): the exchange path takes it
+    hdr2, rec2 = rl.synthetic_las(700_000, 2560, point_format=0, seed=22)
+    want2, _ = rl.oracle_rasterise(hdr2, rec2, 20, levels, with_colors=False)
+    got, overflow, err = _rx_rasterise(cuda_ctx, hdr2, rec2, 20, levels)
+    assert overflow == 0 and err == 0 and (got.view(np.uint32) == want2.view(np.uint32)).all()
 
 
 @pytest.mark.parametrize("fmt,record_len", [(2, None), (3, None), (2, 32)])
