@@ -544,7 +544,15 @@ def _run_gpu_arm(args):
     # (hmrt_trace_opts.full_frame_output + a cudaIpc mapping of rank 0's buffer): the same timed loop, whole frames on rank 0
     gather = None
     if world > 1:
-        shared = [hd.SharedFrames(ctx, POSES, H, W, root=0) for _ in range(2)]
+        shared = []
+        try:
+            shared = [hd.SharedFrames(ctx, POSES, H, W, root=0) for _ in range(2)]
+        except RuntimeError as e:  # raised on every rank alike (hmrt.dist.SharedFrames)
+            for sf in shared:
+                sf.close()
+            shared = []
+            gather = {"unavailable": str(e)}
+    if world > 1 and shared:
         opts_full = hmrt.trace_opts(mh, tile_first=tile_first, tile_stride=tile_stride, full_frame_output=True)
         run_full = run.with_buffers([sf.tensor for sf in shared])
         for cams in timed_batches[:2]:

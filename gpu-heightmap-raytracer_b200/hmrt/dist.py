@@ -107,12 +107,26 @@ class SharedFrames:
         self.root, self.shape = root, (n_frames, H, W, 3)
         nbytes = n_frames * H * W * 3
         handle = bytes(64)
-        self.buf = None
+        self.buf, self.tensor = None, None
+        why = None
         if rank == root:
-            self.buf, handle = ctx.ipc_alloc(nbytes)
+            try:
+                self.buf, handle = ctx.ipc_alloc(nbytes)
+            except _abi.HmrtError as e:
+                why = str(e)
+        ok = all_ranks_agree(why is None, group)
         handles = exchange_handles(handle, group)
-        if rank != root:
-            self.buf = ctx.ipc_open(handles[root], nbytes)
+        if ok and rank != root:
+            try:
+                self.buf = ctx.ipc_open(handles[root], nbytes)
+            except _abi.HmrtError as e:
+                why = str(e)
+        ok = all_ranks_agree(ok and why is None, group)
+        if not ok:  # the same outcome on every rank: nobody is left waiting in a collective
+            if self.buf is not None:
+                self.buf.close()
+                self.buf = None
+            raise RuntimeError(f"shared frames unavailable (cudaIpc): {why or 'refused on another rank'}")
         self.tensor = self.buf.tensor(self.shape)
 
     def close(self, group=None):
