@@ -564,11 +564,45 @@ def _run_gpu_arm(args):
             ctx.trace(W, H, timed_batches[0], opts_full, out=shared[0].tensor)
         run_full.barrier()
         assembled_hash = _frames_hash(torch, shared[0].tensor, 0, 1) if rank == 0 else 0
+        # the same with copy engines instead of in-kernel stores: compact local output, then 2-D peer copies on the step's stream
+        def issue_copy(cams):
+            k = run.issued & 1
+            run.issue(cams, opts)
+            with torch.cuda.stream(run.streams[k]):
+                ctx.copy_tiles_to_frames(run.fbs[k], shared[k].tensor, W, H, POSES, tile_first, tile_stride)
+        for cams in timed_batches[:2]:
+            issue_copy(cams)
+        run.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        c0.record(cur)
+        for s_ in run.streams:
+            s_.wait_event(c0)
+        for _ in range(repeats):
+            for cams in timed_batches:
+                issue_copy(cams)
+        for s_ in run.streams:
+            cur.wait_stream(s_)
+        c1.record(cur)
+        run.barrier()
+        ms_copy = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ms_copy, op=dist.ReduceOp.MAX)
+        ms_copy = float(ms_copy.item())
+        shared[0].tensor.zero_() if rank == 0 else None
+        run.barrier()
+        with torch.cuda.stream(run.streams[0]):
+            ctx.trace(W, H, timed_batches[0], opts, out=run.fbs[0])
+            ctx.copy_tiles_to_frames(run.fbs[0], shared[0].tensor, W, H, POSES, tile_first, tile_stride)
+        run.barrier()
+        copied_hash = _frames_hash(torch, shared[0].tensor, 0, 1) if rank == 0 else 0
         for sf in shared:
             sf.close()
         gather = {"value": rays_per_step * steps_timed / (ms_full * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_full / steps_timed,
                   "bytes_into_rank0_per_step": POSES * W * H * 3 * (world - 1) // world,
                   "assembled_frames_hash": f"{assembled_hash:016x}", "assembled_equals_tiles": assembled_hash == frames_hash,
+                  "copy_engine_variant": {"value": rays_per_step * steps_timed / (ms_copy * 1e-3) / 1e6, "ms_per_step": ms_copy / steps_timed,
+                                          "assembled_equals_tiles": copied_hash == frames_hash,
+                                          "what": "compact local output + hmrt_copy_tiles_to_frames (2-D peer copies on the step's stream) instead of in-kernel stores"},
                   "what": "whole frames assembled on rank 0 inside the timed loop: every rank's traversal kernel stores its 8-row tiles at their place in "
                           "rank 0's frame buffer (cudaIpc peer mapping, 128-bit stores over NVLink); no gather pass, no collective"}
 

@@ -203,6 +203,34 @@ int hmrt_set_l2_persist(hmrt_ctx* ctx, int first_level, float hit_ratio) {
   return 0;
 }
 
+int hmrt_copy_tiles_to_frames(hmrt_ctx* ctx, const uint8_t* d_tiles, uint8_t* d_frames, int W, int H, int n_frames, int tile_first,
+                              int tile_stride) {
+  if (!ctx || !d_tiles || !d_frames || W < 1 || H < 1 || n_frames < 1 || tile_first < 0) return HMRT_E_ARG;
+  const int stride = tile_stride > 0 ? tile_stride : 1;
+  const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
+  if (tile_first >= n_tiles) return 0;
+  hmrt::DeviceGuard guard(ctx->device);
+  const int local_tiles = (n_tiles - tile_first + stride - 1) / stride;
+  const size_t row_bytes = (size_t)W * 3, tile_bytes = row_bytes * HMRT_ROW_TILE;
+  const size_t rows_local = (size_t)hmrt::rows_local(H, tile_first, stride);
+  /* does this shard own the frame's ragged last tile? */
+  const bool owns_last = (n_tiles - 1 - tile_first) % stride == 0 && H % HMRT_ROW_TILE != 0;
+  const int whole = owns_last ? local_tiles - 1 : local_tiles;
+  for (int f = 0; f < n_frames; ++f) {
+    const uint8_t* src = d_tiles + (size_t)f * rows_local * row_bytes;
+    uint8_t* dst = d_frames + (size_t)f * (size_t)H * row_bytes + (size_t)tile_first * tile_bytes;
+    /* local tile j -> frame tile tile_first + j * stride: a 2-D copy, one "row" per tile (copy engine, no SM time) */
+    if (whole > 0)
+      HMRT_CUDA(cudaMemcpy2DAsync(dst, tile_bytes * (size_t)stride, src, tile_bytes, tile_bytes, (size_t)whole, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (owns_last) {
+      const size_t last_rows = (size_t)(H % HMRT_ROW_TILE);
+      HMRT_CUDA(cudaMemcpyAsync(dst + (size_t)whole * tile_bytes * (size_t)stride, src + (size_t)whole * tile_bytes, last_rows * row_bytes,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  return 0;
+}
+
 int hmrt_ipc_alloc(hmrt_ctx* ctx, size_t bytes, void** d_ptr, void* handle64) {
   if (!ctx || !d_ptr || !handle64 || bytes == 0) return HMRT_E_ARG;
   hmrt::DeviceGuard guard(ctx->device);

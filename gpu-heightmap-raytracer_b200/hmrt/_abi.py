@@ -96,6 +96,7 @@ PROTOTYPES = {
     "hmrt_compose_window": (C.c_int, [_P, C.POINTER(WindowSections), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hmrt_broadcast_heightmap": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "hmrt_allreduce_max_heights": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
+    "hmrt_copy_tiles_to_frames": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "hmrt_ipc_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P), _P]),
     "hmrt_ipc_free": (C.c_int, [_P, _P]),
     "hmrt_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),

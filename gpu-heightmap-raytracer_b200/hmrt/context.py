@@ -233,6 +233,13 @@ class Context:
         check(self.lib.hmrt_trace_host(self._h, W, H, cams, n, C.byref(opts), C.c_void_p(ptr)), "hmrt_trace_host")
         return out_host
 
+    def copy_tiles_to_frames(self, tiles, frames, W: int, H: int, n_frames: int, tile_first: int, tile_stride: int):
+        """Compact row-tile output of a sharded trace -> its place in whole frames (possibly peer memory), 2-D device copies."""
+        torch = self._torch
+        self._bind_stream()
+        check(self.lib.hmrt_copy_tiles_to_frames(self._h, self._dev(tiles, torch.uint8, "tiles"), C.c_void_p(frames.data_ptr()), W, H, n_frames,
+                                                 tile_first, tile_stride), "hmrt_copy_tiles_to_frames")
+
     # -- buffers other ranks can map (cudaIpc) -------------------------------------------------
     def ipc_alloc(self, nbytes: int):
         """(IpcBuffer, 64-byte handle): a device buffer of this context that other processes on the box can open."""

@@ -249,6 +249,11 @@ int hmrt_compose_window(hmrt_ctx* ctx, const hmrt_window_sections* sections, int
  * it on this context's device; hmrt_ipc_close / hmrt_ipc_free undo them.  Used for the frame of a row-tile-sharded render
  * (hmrt_trace_opts.full_frame_output): rank 0 allocates the frame, every other rank opens it and renders straight into it. */
 int hmrt_ipc_alloc(hmrt_ctx* ctx, size_t bytes, void** d_ptr, void* handle64);
+/* The other way to assemble a sharded render: copy a call's COMPACT output (d_tiles, the layout of hmrt_trace without
+ * full_frame_output) to its place in whole frames (d_frames: H rows per frame; may be a peer mapping) with 2-D device
+ * copies on the context's stream -- copy engines instead of in-kernel stores (DESIGN.md section 6 compares the two). */
+int hmrt_copy_tiles_to_frames(hmrt_ctx* ctx, const uint8_t* d_tiles, uint8_t* d_frames, int W, int H, int n_frames, int tile_first,
+                              int tile_stride);
 int hmrt_ipc_free(hmrt_ctx* ctx, void* d_ptr);
 int hmrt_ipc_open(hmrt_ctx* ctx, const void* handle64, void** d_ptr);
 int hmrt_ipc_close(hmrt_ctx* ctx, void* d_ptr);

@@ -152,3 +152,22 @@ def test_full_frame_output_layout(cuda_ctx):
     assert torch.equal(buf, whole)
     with pytest.raises(hmrt.HmrtError):
         cuda_ctx.trace_host(W, H, cams, hmrt.trace_opts(sc["max_height"], full_frame_output=True), np.zeros((2, H, W, 3), np.uint8))
+
+
+def test_copy_tiles_to_frames(cuda_ctx):
+    """hmrt_copy_tiles_to_frames: the compact output of every shard copied to its place reassembles the unsharded frames
+    (ragged last tile owned by one of the shards, several frames, W not a multiple of 16)."""
+    import gpulib
+    import hmrt
+
+    sc = ol.scene("r512_l4", seed=5)
+    gpulib.upload_scene(cuda_ctx, sc)
+    for W, H in ((200, 83), (320, 96)):
+        cams = ol.cameras_for(sc, 3)
+        whole, _ = cuda_ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"]))
+        buf = torch.full((3, H, W, 3), 9, dtype=torch.uint8, device="cuda")
+        for r in range(3):
+            part, _ = cuda_ctx.trace(W, H, cams, hmrt.trace_opts(sc["max_height"], tile_first=r, tile_stride=3))
+            cuda_ctx.copy_tiles_to_frames(part, buf, W, H, 3, r, 3)
+        torch.cuda.synchronize()
+        assert torch.equal(buf, whole), (W, H)
