@@ -564,6 +564,7 @@ def _run_gpu_arm(args):
             ctx.trace(W, H, timed_batches[0], opts_full, out=shared[0].tensor)
         run_full.barrier()
         assembled_hash = _frames_hash(torch, shared[0].tensor, 0, 1) if rank == 0 else 0
+        run_full.barrier()  # rank 0 has read its frames before anybody writes into them again
         # the same with copy engines instead of in-kernel stores: compact local output, then 2-D peer copies on the step's stream
         def issue_copy(cams):
             k = run.issued & 1
