@@ -61,9 +61,9 @@ scatter_las_kernel(const uint8_t* __restrict__ records, int64_t n, int record_le
   if (i >= n) return;
   /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
   const RecordHead rh = load_record_head(rec);
-  const double gx = __dadd_rn(__dmul_rn((double)rh.x, sp.scale[0]), sp.offset[0]);
-  const double gy = __dadd_rn(__dmul_rn((double)rh.y, sp.scale[1]), sp.offset[1]);
-  const double gz = __dadd_rn(__dmul_rn((double)rh.z, sp.scale[2]), sp.offset[2]);
+  const double gx = __dadd_rn(__dmul_rn(int_to_double(rh.x), sp.scale[0]), sp.offset[0]);
+  const double gy = __dadd_rn(__dmul_rn(int_to_double(rh.y), sp.scale[1]), sp.offset[1]);
+  const double gz = __dadd_rn(__dmul_rn(int_to_double(rh.z), sp.scale[2]), sp.offset[2]);
   const int cls = sp.cls_off == 15 ? (int)((rh.tail >> 24) & 0x1f) : 0; /* Classification::GetClass(): low 5 bits of byte 15 */
   uint32_t rgb = 0;
   if (keys && sp.rgb_off >= 0) {

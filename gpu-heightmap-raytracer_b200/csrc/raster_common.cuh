@@ -75,14 +75,21 @@ __device__ __forceinline__ bool point_to_cell(const ScatterParams& sp, double gx
   const float fX = div_cell(__double2float_rn(__dsub_rn(gx, sp.mn[0])), sp.cell[0], sp.rcell[0]); /* :200 */
   const float fY = div_cell(__double2float_rn(__dsub_rn(gy, sp.mn[1])), sp.cell[1], sp.rcell[1]); /* :201 */
   fZ = div_cell(__double2float_rn(__dsub_rn(gz, sp.mn[2])), sp.cell[2], sp.rcell[2]);             /* :202 */
-  const float dx = floorf(__fsub_rn(fX, sp.origin[0]));                               /* :205 */
-  const float dy = floorf(__fsub_rn(fY, sp.origin[1]));                               /* :206 */
+  /* :205-209.  floor(t) >= 0 <=> t >= 0 and floor(t) < res0 <=> t < res0 for an integer res0, so the range test runs on t
+   * itself, and for 0 <= t < 2^23 the significand of t + 2^23 rounded toward -inf is floor(t): no FRND / F2I (XU pipe). */
+  const float tx = __fsub_rn(fX, sp.origin[0]), ty = __fsub_rn(fY, sp.origin[1]);
   const float r0 = (float)sp.res0;
-  if (!(dx >= 0.0f && dx < r0 && dy >= 0.0f && dy < r0) || cls == 7) return false;    /* :209 */
-  const uint32_t cx = (uint32_t)(int)dx, cy = (uint32_t)(int)dy;
+  if (!(tx >= 0.0f && tx < r0 && ty >= 0.0f && ty < r0) || cls == 7) return false;
+  const uint32_t cx = __float_as_uint(__fadd_rd(tx, 8388608.0f)) & 0x7fffffu;
+  const uint32_t cy = __float_as_uint(__fadd_rd(ty, 8388608.0f)) & 0x7fffffu;
   cell = cx + cy * (uint32_t)sp.res0;
   if (cx_out) *cx_out = cx, *cy_out = cy;
   return true;
+}
+
+/* (double)int32, exactly, without the XU conversion: 2^52 + 2^31 + x is representable, subtract the bias */
+__device__ __forceinline__ double int_to_double(int32_t x) {
+  return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)), 4503601774854144.0);
 }
 
 /* launch-invariant parameters from the caller's transform; HMRT_E_ARG for a non-positive cell size */

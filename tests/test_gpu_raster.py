@@ -247,3 +247,52 @@ def test_baseline_config_1_end_to_end(cuda_ctx):
         ref = ol.cpu_trace(ol.ref().hmrt_ref_trace, want_pyr, None, 8, 8, W, H, cam, opts)
         ol.assert_same_trace((got[0][0], got[1][0]), ref, "config 1 vs the reference's own code")
     assert (got[1][0]["flags"] & 1).mean() > 0.9
+
+
+def test_gpu_rasteriser_and_window_equal_the_reference_host_code_directly(cuda_ctx):
+    """No restatement in between: the CUDA scatter + mip build + colour resolve against the reference's OWN loader
+    (allocateSection + loadLASToSection, main.cpp:174-269) and hmrt_compose_window against the reference's OWN
+    preparePointBuffer (main.cpp:459-618), both from oracle/_ref/libhmrt_refhost.so (verbatim text, see tests/test_refhost.py)."""
+    import refhostlib
+
+    rh = refhostlib.refhost("")
+    if rh is None:
+        pytest.skip("oracle/_ref/libhmrt_refhost.so not built")
+    coarse, levels = 2, rh.levels
+    res, idx, total = rh.config(coarse)
+    for fmt, origin in [(2, (0.0, 0.0)), (3, (17.0, -9.5)), (0, (0.0, 0.0))]:
+        hdr, rec = rl.synthetic_las(60_000, res[0], point_format=fmt, seed=70 + fmt)
+        rh.set_las(hdr, rec)
+        want_p, want_c = rh.rasterise(origin)
+        got_p, got_c = _gpu_rasterise(cuda_ctx, hdr, rec, coarse, levels, origin=origin)
+        assert (got_p.view(np.uint32) == want_p.view(np.uint32)).all(), (fmt, origin)
+        assert (got_c == want_c).all(), (fmt, origin)
+    # window: the reference's 4 x 4 sections filled with tagged content, the camera somewhere in the inner sections
+    import hmrt
+
+    rng = np.random.default_rng(9)
+    cam0 = np.array([517.25, 33.0, -90.5], np.float32)
+    origins, _, _ = rh.init_sections(cam0)
+    secs = {}
+    for i in range(rh.grid):
+        for j in range(rh.grid):
+            pyr = (rng.random(total, dtype=np.float32) + np.float32(10 * (i * rh.grid + j))).astype(np.float32)
+            col = rng.integers(0, 256, (res[0], res[0], 3), dtype=np.uint8)
+            rh.fill_section(i, j, pyr, col)
+            secs[i, j] = (torch.from_numpy(pyr).cuda(), torch.from_numpy(col).cuda())
+    size = float(coarse << (levels - 1))
+    for k in range(6):
+        cam = np.array([origins[1, 1, 0] + rng.uniform(0, 2 * size * 0.999), 20.0, origins[1, 1, 1] + rng.uniform(0, 2 * size * 0.999)], np.float32)
+        want_cpb, want_pyr, want_col = rh.prepare(cam)
+        pl = hmrt.window_place(cam, origins, rh.grid, coarse, levels)
+        assert np.array_equal(np.array(pl.camera, np.float32).view(np.uint32), want_cpb.view(np.uint32))
+        xs, ys = (pl.min_x, pl.max_x), (pl.min_y, pl.max_y)
+        dp = [[secs[xs[a], ys[b]][0] for b in range(2)] for a in range(2)]
+        dc = [[secs[xs[a], ys[b]][1] for b in range(2)] for a in range(2)]
+        out = torch.empty(total, dtype=torch.float32, device="cuda")
+        out_c = torch.empty((res[0], res[0], 3), dtype=torch.uint8, device="cuda")
+        cuda_ctx.compose_window(dp, dc, coarse, levels, pl.cell_x, pl.cell_y, out, out_c)
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy().view(np.uint32) == want_pyr.view(np.uint32)).all(), k
+        assert (out_c.cpu().numpy() == want_col).all(), k
+    rh.config(1)
