@@ -20,9 +20,16 @@ R0, W, H, POSES = 4096, 1920, 1080, 16
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--l2-gbps", type=float, default=None)
+    ap.add_argument("--l2-gbps", type=float, default=None,
+                    help="L2 read bandwidth of the box; default: the committed measurement of benchmarks/l2_bandwidth.cu (profiles/raw_r01/l2_bandwidth.json)")
     ap.add_argument("--steps", type=int, default=10)
     args = ap.parse_args()
+    l2_source = "--l2-gbps"
+    if args.l2_gbps is None:
+        f = REPO / "profiles" / "raw_r01" / "l2_bandwidth.json"
+        if f.exists():
+            args.l2_gbps = float(json.loads(f.read_text())["l2_read_GBps"])
+            l2_source = "profiles/raw_r01/l2_bandwidth.json (benchmarks/l2_bandwidth.cu, 48 MiB resident set, same pool)"
     ctx = hmrt.Context(0)
     xs = torch.arange(R0, device="cuda", dtype=torch.float32)
     fin0 = (160 + 90 * torch.sin(xs[None, :] * 0.0049) * torch.cos(xs[:, None] * 0.0039) + 35 * torch.sin(xs[None, :] * 0.019 + xs[:, None] * 0.016)
@@ -70,7 +77,7 @@ def main():
                                    "algorithmic_GBps": algo / (ms * 1e-3) / 1e9,
                                    "frac_of_l2_peak": (algo / (ms * 1e-3) / 1e9 / args.l2_gbps) if args.l2_gbps else None}
         del pyr, fb, hits
-    print(json.dumps({"workload": f"{R0}^2 heightmap, {W}x{H}, {POSES} poses per step, 1 GPU", "l2_read_GBps": args.l2_gbps, **out}))
+    print(json.dumps({"workload": f"{R0}^2 heightmap, {W}x{H}, {POSES} poses per step, 1 GPU", "l2_read_GBps": args.l2_gbps, "l2_read_GBps_source": l2_source if args.l2_gbps else None, **out}))
 
 
 if __name__ == "__main__":
