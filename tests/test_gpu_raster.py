@@ -296,3 +296,31 @@ def test_gpu_rasteriser_and_window_equal_the_reference_host_code_directly(cuda_c
         assert (out.cpu().numpy().view(np.uint32) == want_pyr.view(np.uint32)).all(), k
         assert (out_c.cpu().numpy() == want_col).all(), k
     rh.config(1)
+
+
+def test_heights_below_the_header_minimum_and_negative_zero(cuda_ctx):
+    """Points below header.GetMinZ() leave no height (main.cpp:229 on a zero-initialised section) but DO write their colour
+    (:223-224 precede the test); `-0.0f` is the one defined deviation: the reference stores it (sign follows file order),
+    the integer atomicMax leaves +0.0f -- equal values, no sign bit anywhere (tests/test_refhost.py pins the reference side)."""
+    from hmrt import las
+
+    coarse, levels = 1, 8
+    res, idx, total = ol.pyramid_layout(coarse, levels)
+    r0 = res[0]
+    X = np.array([1, 1, 5, 5, 9, 9, 13, 13, 13, 17], np.int32)
+    Y = np.ones(10, np.int32)
+    Z = np.array([-5000, 3000, 4000, -1, -7, -9, 0, 0, 0, -2000], np.int32)
+    rec = las.encode_points(X, Y, Z, 2, np.zeros(10, np.uint8), np.full((10, 3), 65535, np.uint16))
+    hdr = las.LasHeader(2, rec.shape[1], len(X), (1.0, 1.0, 1e-3), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (2.0 * r0, 2.0 * r0, 4.0))
+    want_p, want_c = rl.oracle_rasterise(hdr, rec, coarse, levels)
+    got_p, got_c = _gpu_rasterise(cuda_ctx, hdr, rec, coarse, levels)
+    assert (got_p.view(np.uint32) == want_p.view(np.uint32)).all() and (got_c == want_c).all()
+    assert (got_c[0, 4] == 255).all() and got_p[idx[0]:].reshape(r0, r0)[0, 4] == 0
+    # -0.0f: (float)(-1e-50) == -0.0f
+    hdr2 = las.LasHeader(2, rec.shape[1], 3, (1.0, 1.0, 1e-50), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (2.0 * r0, 2.0 * r0, 4.0))
+    rec2 = las.encode_points(np.array([1, 5, 5], np.int32), np.ones(3, np.int32), np.array([-1, -1, 0], np.int32), 2, np.zeros(3, np.uint8),
+                             np.zeros((3, 3), np.uint16))
+    want2, _ = rl.oracle_rasterise(hdr2, rec2, coarse, levels, with_colors=False)
+    got2, _ = _gpu_rasterise(cuda_ctx, hdr2, rec2, coarse, levels, with_colors=False)
+    assert np.signbit(want2).any() and not np.signbit(got2).any()
+    assert (got2 == want2).all()  # -0.0 == +0.0: the same heights

@@ -288,3 +288,29 @@ def test_rcp_inrange_exhaustive():
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches vs __frcp_rn: 0" in out.stdout
+
+
+def test_height_ramp_outside_0_255_follows_the_host_build(cuda_ctx):
+    """`max_height` BELOW the data (the reference's `-` key lowers it by 100 per press, main.cpp:839-844): the ramp of
+    getHeightColorValue (CudaKernel.cu:38-56) leaves [0, 255] and the float -> unsigned char conversion decides.  The
+    canonical meaning here is the reference's HOST build (truncate to int, keep the low byte: wrap-around), which is what
+    oracle/_ref executes; the reference's own CUDA build would saturate instead -- a documented, deliberate choice
+    (DESIGN.md section 3).  max_height also ends rising rays earlier (:153): both effects must match."""
+    import gpulib
+
+    sc = ol.scene("r512_l4", seed=8)
+    keep = gpulib.upload_scene(cuda_ctx, sc)  # noqa: F841
+    W, H = 256, 160
+    cams = ol.cameras_for(sc, 4)
+    lib = ol.ref() or ol.oracle()
+    fn = lib.hmrt_ref_trace if ol.ref() is not None else lib.hmrt_oracle_trace
+    for frac in (0.5, 0.3):
+        opts = ol.make_opts(sc["max_height"] * frac, shadows=True)
+        rgb, hits = gpulib.gpu_trace(cuda_ctx, W, H, cams, opts)
+        wrapped = 0
+        for i, cam in enumerate(cams):
+            ergb, ehits = ol.cpu_trace(fn, sc["pyramid"], None, sc["coarse"], sc["levels"], W, H, cam, opts)
+            ol.assert_same_trace((rgb[i], hits[i]), (ergb, ehits), f"max_height x {frac}, cam {i}")
+            y = hits[i]["y"][(hits[i]["flags"] & 1) != 0]
+            wrapped += int((y * 2 / (sc["max_height"] * frac) > 2.0).sum())
+        assert wrapped > 100, "the case must actually drive the ramp out of range"
