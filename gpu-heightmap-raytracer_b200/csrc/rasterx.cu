@@ -19,11 +19,10 @@
  * dense finest level (1 GiB per rank at 16384^2, 93 % of it untouched by a rank's own points).  Because pass 1 already
  * sorts by tile, the exchange can move POINTS instead of grids: every rank owns a band of tile rows,
  *
- *   bin: every rank stores the runs of a tile straight into the bucket slices of the rank that OWNS the tile (P2P stores
- *   into peer memory over NVLink, cudaIpc; posted writes, issued from inside the bin kernel: compute and exchange in one
- *   kernel)  ->  barrier  ->  apply: each rank reduces the buckets of its tiles -- all local by now -- into its band  ->
- *   barrier  ->  gather + mip build in ONE kernel: every 128 x 128 tile is read from its owner's band (P2P loads), stored
- *   into the local finest level and reduced to all coarser levels on the way.
+ *   bin (local)  ->  barrier  ->  apply: each rank pulls the pairs of ITS tiles from every rank's buckets over NVLink
+ *   (P2P loads from peer memory, cudaIpc) and reduces them into its band  ->  barrier  ->  gather + mip build in ONE
+ *   kernel: every 128 x 128 tile is read from its owner's band (P2P), stored into the local finest level and reduced to
+ *   all coarser levels on the way.
  *
  * Exchange volume per rank: (N-1)/N of the pairs it owns (8 B per point) + (N-1)/N of the finest level, instead of
  * 2 (N-1)/N of the finest level for the all-reduce, and no separate mip pass.  The barriers are flag exchanges in peer
@@ -66,16 +65,11 @@ struct BinParams {
   const uint8_t* records;
   int64_t n;
   int record_len;
-  int per;                /* records per thread and step: chunk = THREADS * per */
-  /* Destination: the bucket slices live in the region of the rank that OWNS the tile (push model: the bin pass stores its
-   * runs straight into the owner's memory -- local for world 1, NVLink peer stores otherwise).  In every region:
-   * counts[owned tile][slot] u32 and pairs[owned tile][slot][slice_cap], slot = producer rank * CTAs + CTA. */
-  uint8_t* peer[kMaxPeers];
-  size_t counts_off, pairs_off;
-  int tile_row0[kMaxPeers + 1]; /* rank r owns tile rows [tile_row0[r], tile_row0[r + 1]) */
-  int world, rank;
-  uint32_t slots;         /* world * CTAs of the bin pass */
-  uint32_t slice_cap;     /* < 2^24 */
+  int per;                /* records per thread and step: chunk = kBinThreads * per */
+  void* pairs;            /* [n_tiles][n_slices][slice_cap] (cell, height bits) pairs, or -- with colour keys -- (cell, height
+                           * bits, key lo, key hi) quads */
+  uint32_t* counts;       /* [n_tiles][n_slices] */
+  uint32_t slice_cap;
   int tile_shift, tiles_x, n_tiles;
   int* finest;            /* single GPU: overflowing points go straight to the grid; NULL: they are counted in *overflow */
   unsigned long long* keys; /* colour keys next to `finest` (single GPU, KEYS instantiation) */
@@ -119,7 +113,7 @@ __device__ __forceinline__ void apply_pair(int* finest, unsigned long long* keys
 }
 
 /*
- * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][tbase: 256 u64][sdest: chunk u32][spair: chunk pairs]
+ * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][sdest: chunk u32][spair: chunk uint2]
  * [stage 0][stage 1], a stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
  */
 template <int THREADS, bool KEYS>
@@ -130,9 +124,8 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
   uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + 16); /* entries used in this CTA's slice of each bucket (persistent) */
   uint32_t* hist = fill + kMaxTiles;                          /* points of this step per tile */
   uint32_t* offs = hist + kMaxTiles;                          /* exclusive prefix of hist */
-  uint32_t* dest0 = offs + kMaxTiles;                         /* first index of this step's run inside the slice, or ~0u: slice full */
-  unsigned long long* tbase = reinterpret_cast<unsigned long long*>(dest0 + kMaxTiles); /* [256] address of this CTA's slice of every tile (in the owner's region) */
-  uint32_t* sdest = reinterpret_cast<uint32_t*>(tbase + kMaxTiles); /* [chunk] tile << 24 | index inside the slice, per sorted slot */
+  uint32_t* dest0 = offs + kMaxTiles;                         /* first destination index of this step's run, or ~0u: slice full */
+  uint32_t* sdest = dest0 + kMaxTiles;                        /* [chunk] destination pair index per sorted slot */
   Pair* spair = reinterpret_cast<Pair*>((reinterpret_cast<uintptr_t>(sdest + chunk) + 15) & ~(uintptr_t)15); /* [chunk] sorted pairs */
   const uint32_t stage_bytes = ((uint32_t)chunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
   uint8_t* stage0 = reinterpret_cast<uint8_t*>(spair + chunk);
@@ -141,23 +134,10 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
   const uint32_t stage0_s = (uint32_t)__cvta_generic_to_shared(stage0);
   __shared__ uint32_t total_s;
 
-  const uint32_t slot_id = (uint32_t)p.rank * gridDim.x + blockIdx.x;
-  auto slice_index = [&](int t, int& owner) { /* (owned-local tile) * slots + slot, in the region of `owner` */
-    const int ty = t / p.tiles_x;
-    owner = 0;
-    while (owner + 1 < p.world && ty >= p.tile_row0[owner + 1]) ++owner;
-    return (size_t)(t - p.tile_row0[owner] * p.tiles_x) * p.slots + slot_id;
-  };
+  const uint32_t n_slices = gridDim.x;
   for (int t = threadIdx.x; t < kMaxTiles; t += THREADS) {
-    fill[t] = 0;
+    fill[t] = (p.accumulate && t < p.n_tiles) ? p.counts[(size_t)t * n_slices + blockIdx.x] : 0u;
     hist[t] = 0;
-    tbase[t] = 0;
-    if (t < p.n_tiles) {
-      int owner;
-      const size_t si = slice_index(t, owner);
-      tbase[t] = reinterpret_cast<unsigned long long>(p.peer[owner] + p.pairs_off + si * p.slice_cap * sizeof(Pair));
-      if (p.accumulate) fill[t] = __ldcv(reinterpret_cast<const uint32_t*>(p.peer[owner] + p.counts_off) + si);
-    }
   }
   if (threadIdx.x == 0) {
     mbar_init(bar0, 1);
@@ -280,7 +260,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
           offs[t] = run;
           run += h;
           if (f + h <= p.slice_cap) {
-            dest0[t] = f;
+            dest0[t] = (uint32_t)(((size_t)t * n_slices + blockIdx.x) * p.slice_cap + f); /* < 2^32: checked by the launcher */
             fill[t] = f + h;
           } else {
             dest0[t] = 0xffffffffu; /* slice full: this step's points of the tile take the overflow route */
@@ -298,7 +278,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
       const uint32_t tile = slot[q] >> 16, rank = slot[q] & 0xffffu;
       const uint32_t j = offs[tile] + rank, d0 = dest0[tile];
       store_pair(spair + j, cell[q], hb[q], KEYS ? rgb[q] : 0u, p.first_index + c * chunk + (int64_t)(q * THREADS + (int)threadIdx.x));
-      sdest[j] = d0 == 0xffffffffu ? d0 : ((tile << 24) | (d0 + rank));
+      sdest[j] = d0 == 0xffffffffu ? d0 : d0 + rank;
     }
     __syncthreads();
     /* D: write out; consecutive lanes hit consecutive addresses inside a tile's run */
@@ -308,7 +288,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
       const uint32_t d = sdest[j];
       const Pair v = spair[j];
       if (d != 0xffffffffu)
-        reinterpret_cast<Pair*>(tbase[d >> 24])[d & 0xffffffu] = v;
+        static_cast<Pair*>(p.pairs)[d] = v;
       else if (p.finest)
         apply_pair(p.finest, p.keys, v);
       else
@@ -317,22 +297,18 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
     if (dropped) atomicAdd(p.overflow, dropped);
     __syncthreads();
   }
-  for (int t = threadIdx.x; t < p.n_tiles; t += THREADS) {
-    int owner;
-    const size_t si = slice_index(t, owner);
-    reinterpret_cast<uint32_t*>(p.peer[owner] + p.counts_off)[si] = fill[t];
-  }
-  if (p.world > 1) __threadfence_system(); /* the peer stores are performed before the kernel counts as complete */
+  for (int t = threadIdx.x; t < p.n_tiles; t += THREADS) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
 }
 
-/* Pass 2.  The buckets of the owned tiles -- all in this rank's own region, whoever produced them -- reduced into
- * dst[cell - cell_base].  Every thread keeps four 16-byte loads (eight pairs) in flight
+/* Pass 2.  The buckets of the owned tiles, read from every rank's region (own entry = local memory, the others = peer
+ * memory over NVLink), reduced into dst[cell - cell_base].  Every thread keeps four 16-byte loads (eight pairs) in flight
  * before it issues their RED.MAXes.  Slices start 32-byte aligned (slice_cap % 4 == 0). */
 struct ApplyParams {
-  const uint8_t* region;    /* this rank's region: every slice of the tiles it owns is local by now */
+  const uint8_t* peer[kMaxPeers];
   size_t counts_off, pairs_off;
-  uint32_t slice_cap, slots;
-  uint32_t groups_per_tile; /* ceil(slots / slices_per_cta) */
+  uint32_t slice_cap, n_slices, world, rank;
+  uint32_t tile_first;      /* owned tiles are [tile_first, tile_first + gridDim.x / groups_per_tile) */
+  uint32_t groups_per_tile; /* ceil(world * n_slices / slices_per_cta) */
   uint32_t slices_per_cta;
   int* dst;
   uint32_t cell_base;
@@ -341,13 +317,16 @@ struct ApplyParams {
 
 template <bool KEYS>
 __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_constant__ ApplyParams p) {
-  const uint32_t tile = blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile; /* owned-local tile */
+  const uint32_t tile = p.tile_first + blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile;
+  const uint32_t all = p.world * p.n_slices;
   int* __restrict__ dst = p.dst - p.cell_base;
-  const uint8_t* base = p.region;
-  for (uint32_t w = g * p.slices_per_cta; w < min(p.slots, (g + 1) * p.slices_per_cta); ++w) {
-    const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.slots + w);
+  for (uint32_t w = g * p.slices_per_cta; w < min(all, (g + 1) * p.slices_per_cta); ++w) {
+    /* ring order over the sources: at any moment the ranks pull from different peers */
+    const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
+    const uint8_t* base = p.peer[src_rank];
+    const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.n_slices + s);
     if (KEYS) { /* one 16-byte quad per point */
-      const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.slots + w) * p.slice_cap;
+      const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
       for (uint32_t i = threadIdx.x; i < count; i += kBinThreads * 4) {
         uint4 v[4];
 #pragma unroll
@@ -361,7 +340,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
       }
       continue;
     }
-    const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.slots + w) * p.slice_cap;
+    const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
     const uint4* src4 = reinterpret_cast<const uint4*>(src);
     const uint32_t n4 = count >> 1; /* whole 16-byte pieces */
     for (uint32_t i = threadIdx.x; i < n4; i += kBinThreads * 4) {
@@ -454,7 +433,7 @@ static int bin_geometry(int record_len, bool keys, BinGeometry& g) {
   for (;;) {
     g.chunk = g.threads * g.per;
     const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + kMaxTiles * sizeof(unsigned long long) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
+    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
     if (g.smem <= 220 * 1024 || g.per == 1) break;
     g.per >>= 1; /* long records: smaller steps */
   }
@@ -493,7 +472,7 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     const int64_t resident = (int64_t)ctx->sm_count * bg.ctas_per_sm;
     const int n_slices = (int)(chunks < resident ? chunks : resident);
     const int64_t slice_cap = slice_capacity(nb, n_tiles, n_slices);
-    if (slice_cap >= (1 << 24) - 1) return HMRT_E_SHAPE;
+    if ((unsigned long long)n_tiles * (unsigned long long)n_slices * (unsigned long long)slice_cap >= (1ull << 32)) return HMRT_E_SHAPE;
     const size_t counts_bytes = ((size_t)n_tiles * (size_t)n_slices * sizeof(uint32_t) + 255) & ~(size_t)255;
     const size_t need = counts_bytes + (size_t)n_tiles * (size_t)n_slices * (size_t)slice_cap * pair_size;
     if (ctx->ws_cap < need) {
@@ -505,36 +484,34 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     }
     uint8_t* ws = static_cast<uint8_t*>(ctx->d_ws);
     BinParams bp;
-    memset(&bp, 0, sizeof(bp));
     bp.sp = sp;
     bp.records = d_records + first * record_len;
     bp.n = nb;
     bp.record_len = record_len;
     bp.per = bg.per;
-    bp.peer[0] = ws;
-    bp.counts_off = 0;
-    bp.pairs_off = counts_bytes;
-    bp.tile_row0[0] = 0, bp.tile_row0[1] = tiles_x;
-    bp.world = 1, bp.rank = 0;
-    bp.slots = (uint32_t)n_slices;
+    bp.counts = reinterpret_cast<uint32_t*>(ws);
+    bp.pairs = ws + counts_bytes;
+    bp.keys = keys;
+    bp.first_index = first_index + first;
     bp.slice_cap = (uint32_t)slice_cap;
     bp.tile_shift = tile_shift;
     bp.tiles_x = tiles_x;
     bp.n_tiles = n_tiles;
     bp.finest = finest;
-    bp.keys = keys;
     bp.overflow = nullptr;
     bp.accumulate = 0;
-    bp.first_index = first_index + first;
     HMRT_CUDA((cudaError_t)launch_bin(bg, bp, (unsigned)n_slices, ctx->stream));
     HMRT_LAUNCHED(ctx);
     ApplyParams ap;
     memset(&ap, 0, sizeof(ap));
-    ap.region = ws;
+    ap.peer[0] = ws;
     ap.counts_off = 0;
     ap.pairs_off = counts_bytes;
     ap.slice_cap = (uint32_t)slice_cap;
-    ap.slots = (uint32_t)n_slices;
+    ap.n_slices = (uint32_t)n_slices;
+    ap.world = 1;
+    ap.rank = 0;
+    ap.tile_first = 0;
     ap.slices_per_cta = (uint32_t)(g_knob_apply_slices ? g_knob_apply_slices : kSlicesPerApplyCta);
     ap.groups_per_tile = (uint32_t)((n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
     ap.dst = finest;
@@ -612,7 +589,7 @@ int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int worl
   /* the same geometry on every rank: all ranks pass the same (coarse_res, levels, world, max_points_per_rank) */
   rx->n_slices = ctx->sm_count * 2;
   rx->slice_cap = (uint32_t)hmrt::slice_capacity(max_points_per_rank, rx->n_tiles, rx->n_slices);
-  if (rx->slice_cap >= (1u << 24) - 1u) {
+  if ((unsigned long long)rx->n_tiles * (unsigned long long)rx->n_slices * (unsigned long long)rx->slice_cap >= (1ull << 32)) {
     delete rx;
     return HMRT_E_SHAPE;
   }
@@ -624,10 +601,8 @@ int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int worl
     const long long row = (long long)rx->tile_row0[r] * rx->tile;
     rx->band_row0[r] = (int)(row < res[0] ? row : res[0]);
   }
-  /* a region holds the slices of the tiles its rank OWNS, from every producer: (largest band, in tiles) x (world x CTAs) slots */
-  const size_t owned_tiles_max = (size_t)(base + (rem ? 1 : 0)) * rx->tiles_x, slots = (size_t)world * rx->n_slices;
-  const size_t counts_bytes = (owned_tiles_max * slots * sizeof(uint32_t) + 255) & ~(size_t)255;
-  const size_t pairs_bytes = (owned_tiles_max * slots * rx->slice_cap * sizeof(uint2) + 255) & ~(size_t)255;
+  const size_t counts_bytes = ((size_t)rx->n_tiles * rx->n_slices * sizeof(uint32_t) + 255) & ~(size_t)255;
+  const size_t pairs_bytes = ((size_t)rx->n_tiles * rx->n_slices * rx->slice_cap * sizeof(uint2) + 255) & ~(size_t)255;
   /* every rank allocates the LARGEST band so that offsets agree everywhere */
   const size_t band_rows_max = (size_t)(base + (rem ? 1 : 0)) * rx->tile;
   const size_t band_bytes = band_rows_max * (size_t)res[0] * sizeof(float);
@@ -695,8 +670,7 @@ int hmrt_rx_begin(hmrt_rx* rx) {
   hmrt::DeviceGuard guard(rx->ctx->device);
   cudaStream_t st = rx->ctx->stream;
   const size_t band_rows = (size_t)(rx->band_row0[rx->rank + 1] - rx->band_row0[rx->rank]);
-  /* the slice counts need no clearing: the first bin pass of a rasterisation writes every count of every slot it owns, in
-   * whichever region it lives (and a producer may already be writing into THIS region while we are still here) */
+  HMRT_CUDA(cudaMemsetAsync(rx->region + rx->counts_off, 0, (size_t)rx->n_tiles * rx->n_slices * sizeof(uint32_t), st));
   HMRT_CUDA(cudaMemsetAsync(rx->region + offsetof(hmrt::RxHeader, overflow), 0, sizeof(uint32_t), st));
   if (band_rows) HMRT_CUDA(cudaMemsetAsync(rx->region + rx->band_off, 0, band_rows * (size_t)rx->res0 * sizeof(float), st));
   rx->binned_any = false;
@@ -707,15 +681,13 @@ int hmrt_rx_begin(hmrt_rx* rx) {
 int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len, int point_format, const hmrt_las_transform* xf) {
   if (!rx || !xf || n < 0 || point_format < 0 || point_format > 3) return HMRT_E_ARG;
   if (record_len < hmrt::kLasMinLen[point_format] || record_len > 64) return HMRT_E_ARG;
-  /* n == 0 still launches: the pass writes the (zero) counts of this rank's slots into the owners' regions */
-  if (n > 0 && (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15))) return HMRT_E_ARG;
+  if (n == 0) return 0;
+  if (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15)) return HMRT_E_ARG;
   hmrt::DeviceGuard guard(rx->ctx->device);
   hmrt::BinGeometry bg;
   int rc = hmrt::bin_geometry(record_len, false, bg);
   if (rc) return rc;
-  if (!rx->connected) return HMRT_E_STATE; /* the bin pass stores into the owners' regions */
   hmrt::BinParams bp;
-  memset(&bp, 0, sizeof(bp));
   rc = hmrt::fill_scatter_params(xf, rx->res0, bp.sp);
   if (rc) return rc;
   bp.sp.cls_off = 15;
@@ -724,21 +696,17 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   bp.n = n;
   bp.record_len = record_len;
   bp.per = bg.per;
-  for (int r = 0; r < rx->world; ++r) bp.peer[r] = rx->peer[r];
-  bp.counts_off = rx->counts_off;
-  bp.pairs_off = rx->pairs_off;
-  for (int r = 0; r <= rx->world; ++r) bp.tile_row0[r] = rx->tile_row0[r];
-  bp.world = rx->world, bp.rank = rx->rank;
-  bp.slots = (uint32_t)rx->world * (uint32_t)rx->n_slices;
+  bp.counts = reinterpret_cast<uint32_t*>(rx->region + rx->counts_off);
+  bp.pairs = rx->region + rx->pairs_off;
+  bp.keys = nullptr;
+  bp.first_index = 0;
   bp.slice_cap = rx->slice_cap;
   bp.tile_shift = rx->tile_shift;
   bp.tiles_x = rx->tiles_x;
   bp.n_tiles = rx->n_tiles;
   bp.finest = nullptr;
-  bp.keys = nullptr;
   bp.overflow = reinterpret_cast<uint32_t*>(rx->region + offsetof(hmrt::RxHeader, overflow));
   bp.accumulate = rx->binned_any ? 1 : 0;
-  bp.first_index = 0;
   /* always n_slices CTAs: the slice layout is part of the exchange geometry */
   HMRT_CUDA((cudaError_t)hmrt::launch_bin(bg, bp, (unsigned)rx->n_slices, rx->ctx->stream));
   HMRT_LAUNCHED(rx->ctx);
@@ -772,13 +740,16 @@ int hmrt_rx_apply(hmrt_rx* rx) {
   if (rows_owned <= 0) return 0;
   hmrt::ApplyParams ap;
   memset(&ap, 0, sizeof(ap));
-  ap.region = rx->region;
+  for (int r = 0; r < rx->world; ++r) ap.peer[r] = rx->peer[r];
   ap.counts_off = rx->counts_off;
   ap.pairs_off = rx->pairs_off;
   ap.slice_cap = rx->slice_cap;
-  ap.slots = (uint32_t)rx->world * (uint32_t)rx->n_slices;
+  ap.n_slices = (uint32_t)rx->n_slices;
+  ap.world = (uint32_t)rx->world;
+  ap.rank = (uint32_t)rx->rank;
+  ap.tile_first = (uint32_t)(rx->tile_row0[rx->rank] * rx->tiles_x);
   ap.slices_per_cta = (uint32_t)(hmrt::g_knob_apply_slices ? hmrt::g_knob_apply_slices : hmrt::kSlicesPerApplyCta);
-  ap.groups_per_tile = (ap.slots + ap.slices_per_cta - 1) / ap.slices_per_cta;
+  ap.groups_per_tile = (uint32_t)(((unsigned)rx->world * (unsigned)rx->n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
   ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
   ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
   const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;

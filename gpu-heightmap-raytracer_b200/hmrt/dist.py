@@ -192,9 +192,7 @@ class RasterPipeline:
     """clear -> scatter -> exchange -> mip build for one point cloud sharded by contiguous range over the ranks.
 
     mode "single"     one GPU: hmrt_clear_section, hmrt_scatter_las, hmrt_build_mips.
-    mode "peer"       N GPUs, the owner-computes exchange over peer memory (hmrt_rx_*, csrc/rasterx.cu): phases clear,
-                      bin_exchange (binning kernel with P2P stores into the owners' buckets), apply (+ the two barriers),
-                      gather_mips (all-gather of the bands fused with the mip build).
+    mode "peer"       N GPUs, the owner-computes exchange over peer memory (hmrt_rx_*, csrc/rasterx.cu).
     mode "allreduce"  N GPUs, the north star's literal form: private full-size grids + NCCL max all-reduce of the finest
                       level + local mip build.  Taken when the peer path is unavailable on ANY rank (grid shape, cudaIpc
                       refused) or when it reported an overflow; which one ran is in `self.mode` / exchange_description().
@@ -267,9 +265,8 @@ class RasterPipeline:
 
     def exchange_description(self):
         if self.mode == "peer":
-            return ("owner-computes over peer memory (cudaIpc / NVLink): the binning kernel stores each tile's (cell, height) runs straight into the "
-                    "buckets of the rank that owns the tile row (P2P stores), every rank reduces its own buckets, then one kernel all-gathers the "
-                    "finished bands (P2P loads) and builds the mip levels; no NCCL on the data path")
+            return ("owner-computes over peer memory (cudaIpc / NVLink P2P loads): each rank pulls the (cell, height) pairs of the tile rows it "
+                    "owns from every rank's buckets, then one kernel all-gathers the finished bands and builds the mip levels; no NCCL on the data path")
         if self.mode == "allreduce":
             why = f" (peer path unavailable: {self.peer_failure})" if self.peer_failure else ""
             return "NCCL max all-reduce of the dense finest level on its int32 view + local mip build" + why
@@ -295,7 +292,7 @@ class RasterPipeline:
 
         lib, ctx = self.ctx.lib, self.ctx
         if self.mode == "peer":
-            self.PHASES = ("clear", "bin_exchange", "apply", "gather_mips")
+            self.PHASES = ("clear", "bin", "exchange_apply", "gather_mips")
             ctx._bind_stream()
             mark()
             check(lib.hmrt_rx_begin(self.rx), "hmrt_rx_begin")

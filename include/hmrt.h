@@ -283,12 +283,12 @@ int hmrt_allreduce_max_heights(hmrt_ctx* ctx, void* nccl_comm, float* d_pyramid,
  * Multi-GPU rasterisation as an owner-computes exchange over PEER MEMORY (NVLink P2P through cudaIpc; csrc/rasterx.cu) -- the
  * faster equivalent of "scatter into a private grid, hmrt_allreduce_max_heights, hmrt_build_mips": points are sharded by
  * contiguous range (main.cpp:193's file order), every rank OWNS a band of rows of the finest level, and what travels is
- * the points' (cell, height) pairs -- stored by the binning kernel straight into the owner's memory -- plus one all-gather
- * of the finished bands that is fused with the mip build.  Bit-identical to one GPU (max is associative, commutative, idempotent).  One hmrt_rx per rank; all ranks pass the
+ * the points' (cell, height) pairs to the owner plus one all-gather of the finished bands that is fused with the mip
+ * build.  Bit-identical to one GPU (max is associative, commutative, idempotent).  One hmrt_rx per rank; all ranks pass the
  * same (coarse_res, levels, world, max_points_per_rank) and make the same sequence of calls:
  *
  *     hmrt_rx_create; hmrt_rx_export -> exchange the 64-byte handles (any transport) -> hmrt_rx_connect          (once)
- *     hmrt_rx_begin; hmrt_rx_bin (1..n times, also with n = 0); hmrt_rx_barrier; hmrt_rx_apply; hmrt_rx_barrier; hmrt_rx_gather_mips   (per cloud)
+ *     hmrt_rx_begin; hmrt_rx_bin (1..n times); hmrt_rx_barrier; hmrt_rx_apply; hmrt_rx_barrier; hmrt_rx_gather_mips   (per cloud)
  *     hmrt_rx_status -> overflow must be 0 on every rank (else: rerun with a larger max_points_per_rank or use the all-reduce path)
  *
  * Everything is asynchronous on the context's stream except hmrt_rx_status; the barriers are flag exchanges in peer memory
