@@ -119,7 +119,7 @@ def measure(torch, dist, hmrt, ctx, rank, world, points, hbm_peak, reps=3):
     if rank != 0:
         return None
     algo = points * (REC_LEN + 4) / world  # per GPU: read the record, one 4-byte atomic max
-    scatter_ms = phases.get("scatter", 0.0) + phases.get("bin", 0.0) + phases.get("apply", 0.0)
+    scatter_ms = phases.get("scatter", 0.0) + phases.get("bin", 0.0) + phases.get("exchange_apply", 0.0)
     return {
         "workload": f"{points} LAS format-{FMT} points ({REC_LEN} B records, uniformly scattered: no spatial order) -> {R0}^2 grid, "
                     f"sharded by contiguous point range over {world} GPU(s)",
