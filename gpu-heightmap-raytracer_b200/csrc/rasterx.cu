@@ -39,7 +39,6 @@ namespace hmrt {
 constexpr int kBinThreads = 256; /* CTA size of the apply pass; the bin pass is instantiated for 256 and 512 threads */
 constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles */
 constexpr int kMaxPer = 8;     /* records per thread and step */
-constexpr int kSlicesPerApplyCta = 2; /* default; see ApplyParams::slices_per_cta.  Few slices per CTA = many CTAs per tile = few tiles in flight: the grid under them stays in L2 */
 constexpr int kMaxPeers = 16;
 constexpr size_t kHeaderBytes = 4096;
 
@@ -308,60 +307,71 @@ struct ApplyParams {
   size_t counts_off, pairs_off;
   uint32_t slice_cap, n_slices, world, rank;
   uint32_t tile_first;      /* owned tiles are [tile_first, tile_first + gridDim.x / groups_per_tile) */
-  uint32_t groups_per_tile; /* ceil(world * n_slices / slices_per_cta) */
-  uint32_t slices_per_cta;
+  uint32_t groups_per_tile; /* CTAs per tile: ceil(world * n_slices * pieces_per_slice / warps per CTA) */
+  uint32_t pieces_per_slice; /* ceil(slice_cap / kApplyPiece) */
   int* dst;
   uint32_t cell_base;
   unsigned long long* keys; /* KEYS instantiation (single GPU): colour keys, indexed like dst */
 };
 
+/* A WARP's unit of work is one piece of kApplyPiece pairs of one slice (4 trips of 32 lanes x 16 bytes x 2 pairs): slices
+ * shrink with the number of ranks (825 pairs each at 8 GPUs), and a whole CTA per slice left most lanes idle there.  The
+ * pieces of a tile are numbered slice-major, so the warps of a CTA read neighbouring memory; many CTAs per tile = few
+ * tiles in flight = the grid under them stays in L2. */
+constexpr uint32_t kApplyPiece = 1024;
+
 template <bool KEYS>
 __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_constant__ ApplyParams p) {
   const uint32_t tile = p.tile_first + blockIdx.x / p.groups_per_tile, g = blockIdx.x % p.groups_per_tile;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t all = p.world * p.n_slices;
+  const uint32_t item = g * (kBinThreads / 32) + warp; /* piece number inside the tile */
+  const uint32_t w = item / p.pieces_per_slice, piece = item - w * p.pieces_per_slice;
+  if (w >= all) return;
   int* __restrict__ dst = p.dst - p.cell_base;
-  for (uint32_t w = g * p.slices_per_cta; w < min(all, (g + 1) * p.slices_per_cta); ++w) {
-    /* ring order over the sources: at any moment the ranks pull from different peers */
-    const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
-    const uint8_t* base = p.peer[src_rank];
-    const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.n_slices + s);
-    if (KEYS) { /* one 16-byte quad per point */
-      const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
-      for (uint32_t i = threadIdx.x; i < count; i += kBinThreads * 4) {
-        uint4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t j = i + (uint32_t)k * kBinThreads;
-          v[k] = j < count ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (i + (uint32_t)k * kBinThreads < count) apply_pair(dst, p.keys, v[k]);
-      }
-      continue;
-    }
-    const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
-    const uint4* src4 = reinterpret_cast<const uint4*>(src);
-    const uint32_t n4 = count >> 1; /* whole 16-byte pieces */
-    for (uint32_t i = threadIdx.x; i < n4; i += kBinThreads * 4) {
+  /* ring order over the sources: at any moment the ranks pull from different peers */
+  const uint32_t src_rank = (w / p.n_slices + p.rank) % p.world, s = w % p.n_slices;
+  const uint8_t* base = p.peer[src_rank];
+  const uint32_t count = __ldcv(reinterpret_cast<const uint32_t*>(base + p.counts_off) + (size_t)tile * p.n_slices + s);
+  const uint32_t lo = piece * kApplyPiece;
+  if (lo >= count) return;
+  const uint32_t hi = min(count, lo + kApplyPiece);
+  if (KEYS) { /* one 16-byte quad per point */
+    const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
+    for (uint32_t i = lo + lane; i < hi; i += 32 * 4) {
       uint4 v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t j = i + (uint32_t)k * kBinThreads;
-        v[k] = j < n4 ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t j = i + (uint32_t)k * 32;
+        v[k] = j < hi ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (i + (uint32_t)k * kBinThreads < n4) {
-          atomicMax(dst + v[k].x, (int)v[k].y);
-          atomicMax(dst + v[k].z, (int)v[k].w);
-        }
+      for (int k = 0; k < 4; ++k)
+        if (i + (uint32_t)k * 32 < hi) apply_pair(dst, p.keys, v[k]);
+    }
+    return;
+  }
+  const uint2* src = reinterpret_cast<const uint2*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
+  const uint4* src4 = reinterpret_cast<const uint4*>(src); /* lo is even: pieces start 16-byte aligned */
+  const uint32_t q_lo = lo >> 1, q_hi = hi >> 1; /* whole 16-byte pieces of two pairs */
+  for (uint32_t i = q_lo + lane; i < q_hi; i += 32 * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = i + (uint32_t)k * 32;
+      v[k] = j < q_hi ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i + (uint32_t)k * 32 < q_hi) {
+        atomicMax(dst + v[k].x, (int)v[k].y);
+        atomicMax(dst + v[k].z, (int)v[k].w);
       }
     }
-    if ((count & 1u) && threadIdx.x == 0) {
-      const uint2 v = __ldcs(src + (count - 1));
-      atomicMax(dst + v.x, (int)v.y);
-    }
+  }
+  if ((hi & 1u) && lane == 0) { /* only the last piece of a slice can end on an odd count */
+    const uint2 v = __ldcs(src + (hi - 1));
+    atomicMax(dst + v.x, (int)v.y);
   }
 }
 
@@ -512,8 +522,8 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     ap.world = 1;
     ap.rank = 0;
     ap.tile_first = 0;
-    ap.slices_per_cta = (uint32_t)(g_knob_apply_slices ? g_knob_apply_slices : kSlicesPerApplyCta);
-    ap.groups_per_tile = (uint32_t)((n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
+    ap.pieces_per_slice = ((uint32_t)slice_cap + kApplyPiece - 1) / kApplyPiece;
+    ap.groups_per_tile = ((uint32_t)n_slices * ap.pieces_per_slice + (kBinThreads / 32) - 1) / (kBinThreads / 32);
     ap.dst = finest;
     ap.cell_base = 0;
     ap.keys = keys;
@@ -748,8 +758,8 @@ int hmrt_rx_apply(hmrt_rx* rx) {
   ap.world = (uint32_t)rx->world;
   ap.rank = (uint32_t)rx->rank;
   ap.tile_first = (uint32_t)(rx->tile_row0[rx->rank] * rx->tiles_x);
-  ap.slices_per_cta = (uint32_t)(hmrt::g_knob_apply_slices ? hmrt::g_knob_apply_slices : hmrt::kSlicesPerApplyCta);
-  ap.groups_per_tile = (uint32_t)(((unsigned)rx->world * (unsigned)rx->n_slices + ap.slices_per_cta - 1) / ap.slices_per_cta);
+  ap.pieces_per_slice = (rx->slice_cap + hmrt::kApplyPiece - 1) / hmrt::kApplyPiece;
+  ap.groups_per_tile = ((uint32_t)rx->world * (uint32_t)rx->n_slices * ap.pieces_per_slice + (hmrt::kBinThreads / 32) - 1) / (hmrt::kBinThreads / 32);
   ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
   ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
   const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;
