@@ -180,6 +180,13 @@ int hmrt_set_host_variant(hmrt_ctx* ctx, int variant) {
   return 0;
 }
 
+/* development knob (not in include/hmrt.h): row segments per frame of the streamed hmrt_trace_host schedule, 0 = built-in */
+int hmrt_debug_host_segments(hmrt_ctx* ctx, int segments) {
+  if (!ctx || segments < 0 || segments > 4) return HMRT_E_ARG;
+  ctx->host_segments = segments;
+  return 0;
+}
+
 int hmrt_set_window_variant(hmrt_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;
   ctx->window_variant = variant;

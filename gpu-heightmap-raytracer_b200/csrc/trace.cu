@@ -44,7 +44,7 @@ struct TraceScratch {
   uint32_t pad;
 };
 
-constexpr int kSegments = 4; /* row segments per frame whose completion is signalled separately */
+constexpr int kMaxSegments = 4; /* row segments per frame whose completion can be signalled separately (TraceParams::segments of them) */
 struct SegDone {
   uint32_t units; /* 8 x 4 tiles of the segment stored so far */
   uint32_t flag;  /* 1 once all of them are (polled by cuStreamWaitValue32 on the copy stream) */
@@ -73,7 +73,8 @@ struct TraceParams {
   unsigned long long* stats;       /* instrumented kernels only: {rays, loop iterations, air-phase iterations} accumulated */
   /* hmrt_trace_host: completion tracking per (frame, row segment) so that the device->host copy of a segment can start the
    * moment its last tile is stored, while the same launch is still tracing the rest (null: no tracking) */
-  SegDone* seg_done;               /* [frames * kSegments] */
+  SegDone* seg_done;               /* [frames * segments] */
+  uint32_t segments;               /* row segments per frame (1 .. kMaxSegments) */
   uint32_t strips_per_frame;       /* chunks_per_frame / chunks_x */
   /* up to kInlineFrames per-frame constants ride in the kernel parameters: no host->device copy in front
    * of the launch (a 16-frame call spent ~27 us of device timeline on that copy) */
@@ -246,10 +247,10 @@ __device__ __forceinline__ void trace_unit(const TraceParams& p, uint32_t tab, f
       /* everything is recomputed from the chunk number: nothing extra stays live across the walk */
       const uint32_t frame_n = chunk / p.chunks_per_frame;
       const uint32_t strip_n = p.strips_per_frame - 1u - (chunk - frame_n * p.chunks_per_frame) / p.chunks_x;
-      const uint32_t seg = strip_n * (uint32_t)kSegments / p.strips_per_frame;
-      const uint32_t s_lo = (seg * p.strips_per_frame + kSegments - 1) / kSegments, s_hi = ((seg + 1) * p.strips_per_frame + kSegments - 1) / kSegments;
+      const uint32_t seg = strip_n * p.segments / p.strips_per_frame;
+      const uint32_t s_lo = (seg * p.strips_per_frame + p.segments - 1) / p.segments, s_hi = ((seg + 1) * p.strips_per_frame + p.segments - 1) / p.segments;
       const uint32_t want = (s_hi - s_lo) * p.chunks_x * 4u, mine = (uint32_t)(k_last - k_first);
-      SegDone* sd = p.seg_done + frame_n * kSegments + seg;
+      SegDone* sd = p.seg_done + frame_n * p.segments + seg;
       __threadfence(); /* the tile's stores (ordered before this lane by the __syncwarp) before the count */
       if (atomicAdd(&sd->units, mine) + mine == want) {
         __threadfence_system();
@@ -402,7 +403,7 @@ static int ensure_frames(hmrt_ctx* ctx, int n) {
  * points at the first row of local tile `tile_lo`. */
 static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, int frames_at, int W, int H, const hmrt_camera* cams,
                         int n_frames, const hmrt_trace_opts* opts, uint8_t* d_rgb, hmrt_hit* d_hits, int tile_lo = 0, int tile_cnt = 0,
-                        SegDone* seg_done = nullptr, bool overlapped = false) {
+                        SegDone* seg_done = nullptr, bool overlapped = false, int segments = 1) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   if (opts->tile_first >= n_tiles) return 0; /* nothing to render on this rank */
@@ -486,6 +487,7 @@ static int launch_trace(hmrt_ctx* ctx, cudaStream_t stream, int base, int slot, 
   const void* fn = pick_kernel(d_hits != nullptr, walk, tailed, notify);
   const int kslot = (notify ? 16 : 0) + (tailed ? 8 : 0) + (d_hits ? 4 : 0) + walk;
   p.seg_done = notify ? seg_done : nullptr;
+  p.segments = (uint32_t)segments;
   p.strips_per_frame = p.chunks_per_frame / p.chunks_x;
   if (ctx->ctas_per_sm[kslot] == 0) {
     int per_sm = 0;
@@ -607,7 +609,10 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
   if (local_tiles == 0) return 0;
   const uint32_t strips = (uint32_t)local_tiles * 2u;
   const size_t row_bytes = (size_t)W * 3, rows_total = frame_bytes / row_bytes;
-  const int n_seg = n_frames * hmrt::kSegments;
+  /* a single frame is latency-bound: release it in quarters; a batch is bound by the device->host link, where every stream
+   * memory operation in front of a copy costs ~25 us of copy-stream time: one flag per frame */
+  const int segs = ctx->host_segments > 0 ? ctx->host_segments : (n_frames == 1 ? hmrt::kMaxSegments : 1);
+  const int n_seg = n_frames * segs;
   if (ctx->seg_cap < n_seg) {
     if (ctx->d_seg_done) HMRT_CUDA(cudaFree(ctx->d_seg_done));
     ctx->d_seg_done = nullptr;
@@ -627,7 +632,7 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
   for (int l = 0; l < n_launches; ++l) {
     const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
     rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0,
-                            sd + (size_t)f0 * hmrt::kSegments);
+                            sd + (size_t)f0 * segs, false, segs);
     if (rc) break;
   }
   /* the safety net goes in even when a launch failed: the waits below must always be released */
@@ -639,13 +644,13 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
   }
   if (rc) return rc;
   for (int f = 0; f < n_frames; ++f)
-    for (int seg = hmrt::kSegments - 1; seg >= 0; --seg) { /* rows are traced from the top of the frame down */
-      const uint32_t s_lo = ((uint32_t)seg * strips + hmrt::kSegments - 1) / hmrt::kSegments,
-                     s_hi = (((uint32_t)seg + 1u) * strips + hmrt::kSegments - 1) / hmrt::kSegments;
+    for (int seg = segs - 1; seg >= 0; --seg) { /* rows are traced from the top of the frame down */
+      const uint32_t s_lo = ((uint32_t)seg * strips + (uint32_t)segs - 1) / (uint32_t)segs,
+                     s_hi = (((uint32_t)seg + 1u) * strips + (uint32_t)segs - 1) / (uint32_t)segs;
       if (s_hi <= s_lo) continue;
       const size_t r0 = (size_t)s_lo * 4, r1 = (size_t)s_hi * 4 < rows_total ? (size_t)s_hi * 4 : rows_total;
       if (r1 <= r0) continue;
-      const unsigned long long flag = reinterpret_cast<unsigned long long>(&sd[(size_t)f * hmrt::kSegments + seg].flag);
+      const unsigned long long flag = reinterpret_cast<unsigned long long>(&sd[(size_t)f * segs + seg].flag);
       const int drc = wait_value(ctx->copy_stream, flag, 1u, 0u);
       if (drc != 0) return 999; /* cudaErrorUnknown: the driver refused the stream memory operation */
       const size_t off = (size_t)f * frame_bytes + r0 * row_bytes;
@@ -693,7 +698,11 @@ static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_
   for (int l = 0; l < whole; ++l) {
     const int f0 = l * group, nf = (n_frames - f0 < group) ? n_frames - f0 : group;
     cudaStream_t st = ctx->frame_stream[l & 1];
-    rc = hmrt::launch_trace(ctx, st, base, l, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr);
+    /* the launches alternate between two streams, i.e. each one's drain runs under the next one's head: the lean kernel
+     * without the tile-granular tail (see launch_trace), except for the very last whole launch of the call */
+    const bool overlapped = l + 1 < whole || split_last;
+    rc = hmrt::launch_trace(ctx, st, base, l, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0, nullptr,
+                            overlapped);
     if (rc) return rc;
     HMRT_CUDA(cudaEventRecord(ctx->frame_event[l & 1], st));
     HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[l & 1], 0));
@@ -744,10 +753,12 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
     }
     HMRT_CUDA(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
   }
-  /* Schedules (measured on B200, 4K frames, profiles/raw_r02/trace_host_variants.txt): batches of frames are bound by the
-   * device->host link (398 MB per 16-frame step at ~45 GB/s > the 8 ms of traversal), where the per-group schedule is as
-   * good as it gets and the 64 stream operations of the streamed one cost 4 %; a SINGLE frame is latency-bound, where
-   * releasing each quarter frame as it completes wins 6 % (0.90 vs 0.96 ms).  Variant 0 picks accordingly. */
+  /* Schedules (measured on B200, 4K frames, profiles/raw_r02/trace_host_variants.txt): for a batch of frames the per-group
+   * schedule (one lean launch per frame on alternating streams, each followed by its copy) takes 8.83 ms per 16-frame step
+   * against 8.00 ms for the traversal alone and 7.13 ms for the copies alone (55.8 GB/s, the Gen5 x16 link); the streamed
+   * schedule takes 9.2-9.5 ms whatever the segment count (its kernel alone is 6 % slower: a fence and an atomic per unit of
+   * work).  A SINGLE frame is latency-bound, where releasing each quarter frame as it completes wins 6 % (0.90 vs 0.96 ms).
+   * Variant 0 picks accordingly. */
   const bool streamed = ctx->host_variant == 2 || (ctx->host_variant == 0 && n_frames == 1);
   stream_wait_value32_fn wait_value = streamed ? stream_wait_value32() : nullptr;
   if (wait_value)
