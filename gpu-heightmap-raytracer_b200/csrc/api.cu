@@ -180,10 +180,16 @@ int hmrt_set_host_variant(hmrt_ctx* ctx, int variant) {
   return 0;
 }
 
-/* development knob (not in include/hmrt.h): row segments per frame of the streamed hmrt_trace_host schedule, 0 = built-in */
+/* development knobs (not in include/hmrt.h): row segments per frame of the streamed hmrt_trace_host schedule; frame groups per
+ * middle launch of the per-group schedule.  0 = built-in. */
 int hmrt_debug_host_segments(hmrt_ctx* ctx, int segments) {
   if (!ctx || segments < 0 || segments > 4) return HMRT_E_ARG;
   ctx->host_segments = segments;
+  return 0;
+}
+int hmrt_debug_host_mid_groups(hmrt_ctx* ctx, int groups) {
+  if (!ctx || groups < 0 || groups > 64) return HMRT_E_ARG;
+  ctx->host_mid_groups = groups;
   return 0;
 }
 

@@ -43,6 +43,7 @@ struct hmrt_ctx {
   unsigned long long* d_stats; /* counters of the instrumented kernels (hmrt_trace_stats) */
   void* d_seg_done;   /* SegDone[seg_cap]: per-(frame, row segment) completion of hmrt_trace_host's streaming form */
   int seg_cap;
+  int host_mid_groups; /* development knob: frame groups per middle launch of the per-group host schedule (0 = built-in 2) */
   int host_segments;  /* development knob: row segments per frame of the streamed host schedule (0 = built-in) */
   int host_variant;   /* hmrt_trace_host: 0 = auto, 1 = one launch per frame group, 2 = streamed (segment flags + stream memory operations) */
   int window_variant; /* 0 = TMA bulk-copy gather where the planes qualify, 1 = per-thread 128-bit gather (hmrt_set_window_variant) */
