@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--points", type=int, default=500_000_000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--modes", default="peer,single,direct")
-    ap.add_argument("--variants", default="", help="bin_threads:bin_per:apply_slices,... (development knobs; peer mode only)")
+    ap.add_argument("--variants", default="", help="bin_threads:bin_per:apply_slices[:1 = generic bin kernel],... (development knobs; peer mode only)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ctx = hmrt.Context(0)
@@ -48,8 +48,8 @@ def main():
         rp.close()
     ctx.set_scatter_mode(0)
     for v in [v for v in args.variants.split(",") if v]:
-        th, per, sl = [int(x) for x in v.split(":")]
-        for key, val in ((0, th), (1, per), (2, sl)):
+        th, per, sl, generic = ([int(x) for x in v.split(":")] + [0])[:4]
+        for key, val in ((0, th), (1, per), (2, sl), (3, generic)):
             assert ctx.lib.hmrt_debug_raster_knob(key, val) == 0
         rp = hd.RasterPipeline(ctx, rpl.COARSE, rpl.LEVELS, single=True, force_mode="peer")
         best = None
@@ -60,7 +60,7 @@ def main():
         out["variant_" + v] = {**best, "total_ms": sum(best.values())}
         hashes["variant_" + v] = rpl.finest_hash(torch, pyr[idx[0]:])
         rp.close()
-    for key in (0, 1, 2):
+    for key in (0, 1, 2, 3):
         ctx.lib.hmrt_debug_raster_knob(key, 0)
     out["hashes_equal"] = len(set(hashes.values())) == 1
     print(json.dumps(out))

@@ -210,11 +210,11 @@ int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int rec
   int* finest = reinterpret_cast<int*>(d_pyramid + idx[0]);
 
   /* ---- choose the path: tile-binned (rasterx.cu) for large, spatially unordered clouds on grids beyond L2 ---- */
-  const int tile_shift = hmrt::binned_tile_shift(res[0]);
+  const int tile_shift = hmrt::binned_tile_shift(res[0], 1);
   const int tiles_x = (res[0] + (1 << tile_shift) - 1) >> tile_shift;
   const int n_tiles = tiles_x * tiles_x;
   bool binned = false;
-  const bool binnable = n_tiles >= 64 && (reinterpret_cast<uintptr_t>(d_records) & 15) == 0 && record_len <= 64;
+  const bool binnable = n_tiles >= 16 && (reinterpret_cast<uintptr_t>(d_records) & 15) == 0 && record_len <= 64;
   if (binnable && ctx->scatter_mode == 2) binned = true; /* forced (tests, benchmarks) */
   if (binnable && ctx->scatter_mode == 0 && n >= (int64_t)1 << 22 && (size_t)res[0] * res[0] * 4 > ((size_t)96 << 20)) {
     /* the probe costs one stream synchronisation: once per input (first_index == 0), later chunks of the same file reuse the verdict */

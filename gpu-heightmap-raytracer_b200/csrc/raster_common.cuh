@@ -223,7 +223,7 @@ __device__ __forceinline__ void mips_tile(const MipParams& mp, const float* __re
 #endif
 
 /* ---- tile-binned path (rasterx.cu), also used by hmrt_scatter_las for unordered clouds ---------------------------- */
-int binned_tile_shift(int res0);
+int binned_tile_shift(int res0, int world);
 /* Bin + apply n records into `finest` (single GPU: overflowing points go straight to the grid). */
 int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, const ScatterParams& sp, int* finest,
                           unsigned long long* keys, int64_t first_index);

@@ -37,15 +37,21 @@
 namespace hmrt {
 
 constexpr int kBinThreads = 256; /* CTA size of the apply pass; the bin pass is instantiated for 256 and 512 threads */
-constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles */
+constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles (usually 8 x 8) */
 constexpr int kMaxPer = 8;     /* records per thread and step */
 constexpr int kMaxPeers = 16;
 constexpr size_t kHeaderBytes = 4096;
 
-/* smallest shift with ceil(res0 / 2^shift) <= 16 */
-int binned_tile_shift(int res0) {
+/* Tile side = 2^shift.  The apply pass wants the grid under a tile to sit in L2 (16 MB = 2048^2 cells measured fine, 64 MB
+ * twice as slow), the bin pass wants few tiles (64 instead of 256: 3.12 -> 2.72 ms for 500 M points,
+ * profiles/raw_r02/raster_tiles_per_axis.json): ceil(res0 / 2048) tiles per axis, at least 8, at most 16 (kMaxTiles).  The
+ * exchange deals out whole tile rows, so a world size that does not divide 8 keeps 16 rows. */
+int binned_tile_shift(int res0, int world) {
+  int per_axis = (res0 + 2047) / 2048;
+  per_axis = per_axis < 8 ? 8 : per_axis > 16 ? 16 : per_axis;
+  if (8 % world != 0) per_axis = 16;
   int s = 0;
-  while (((res0 + (1 << s) - 1) >> s) > 16) ++s;
+  while (((res0 + (1 << s) - 1) >> s) > per_axis) ++s;
   return s;
 }
 
@@ -74,6 +80,7 @@ struct BinParams {
   unsigned long long* keys; /* colour keys next to `finest` (single GPU, KEYS instantiation) */
   uint32_t* overflow;
   int accumulate;         /* continue the slices of an earlier call of the same rasterisation */
+  uint32_t cta_rot;       /* chunk c goes to CTA (c + cta_rot) % grid: successive small calls fill different slices */
   int64_t first_index;    /* colour keys: file index of record 0 (main.cpp:223-224: the last writer in file order wins) */
 };
 
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
     if (threadIdx.x < bytes - bulk) stage0[(size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
   };
 
-  int64_t c = blockIdx.x;
+  int64_t c = (blockIdx.x + gridDim.x - p.cta_rot % gridDim.x) % gridDim.x; /* slices stay indexed by blockIdx.x */
   if (c < n_chunks) issue(c, 0);
   __syncthreads();
   for (int k = 0; c < n_chunks; ++k, c += gridDim.x) {
@@ -297,6 +304,222 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
     __syncthreads();
   }
   for (int t = threadIdx.x; t < p.n_tiles; t += THREADS) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
+}
+
+/*
+ * Pass 1, the instantiation that runs on the usual input: 512 threads x 4 records per step, power-of-two cell sizes (the
+ * reference's 2.0) -- everything the generic kernel above tests per point is a compile-time fact here, so the four decodes
+ * of a thread are one straight-line block.  Same slices, same counts, same pairs (the order inside a run may differ: max
+ * does not care).  Differences in the step:
+ *   - the prefix over the tiles is computed by eight warps at once (each derives the full prefix from two 16-byte loads
+ *     per lane and owns one tile per lane for the slice bookkeeping) instead of by one warp while fifteen wait;
+ *   - the histogram is double buffered, so clearing it needs no barrier of its own;
+ *   - every shared-memory access is an LDS / STS on a compile-time offset of the dynamic window (the generic kernel's
+ *     aligned-up pointers made the sorted pairs generic LD / ST).
+ * Shared memory: [2 mbarriers][fill 256][hist 2 x 256][offs, dest0 256 x 2][sdest 2048][spair 2048][stage 0][stage 1].
+ */
+constexpr int kFastThreads = 512, kFastPer = 4, kFastChunk = kFastThreads * kFastPer;
+constexpr uint32_t kFastFill = 16, kFastHist = kFastFill + 4 * kMaxTiles, kFastOffd = kFastHist + 8 * kMaxTiles,
+                   kFastSdest = kFastOffd + 8 * kMaxTiles, kFastSpair = kFastSdest + 4 * kFastChunk;
+template <bool KEYS> __host__ __device__ constexpr uint32_t fast_stage0() { return (kFastSpair + (uint32_t)sizeof(typename PairOf<KEYS>::type) * kFastChunk + 127u) & ~127u; }
+
+template <bool KEYS, bool ALIGNED, bool FULL>
+__device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* stage, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
+                                            uint32_t (&hb)[kFastPer], uint32_t (&slot)[kFastPer], uint32_t (&rgb)[kFastPer]) {
+  const float r0f = (float)p.sp.res0;
+  const double bias = 4503601774854144.0; /* 2^52 + 2^31 */
+  /* three passes over the thread's four records -- loads, arithmetic, ranks -- so that their latencies overlap */
+  int32_t X[kFastPer], Y[kFastPer], Z[kFastPer];
+  uint32_t tail[kFastPer];
+#pragma unroll
+  for (int q = 0; q < kFastPer; ++q) {
+    const int i = q * kFastThreads + (int)threadIdx.x;
+    X[q] = Y[q] = Z[q] = 0;
+    tail[q] = 7u << 24; /* past the end of the input: rejected like a class-7 point */
+    if (FULL || i < count) {
+      const uint32_t off = (uint32_t)i * (uint32_t)p.record_len;
+      if (ALIGNED) { /* 20 / 28-byte records: X, Y, Z and the flags word are aligned words */
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + off);
+        X[q] = (int32_t)w[0], Y[q] = (int32_t)w[1], Z[q] = (int32_t)w[2], tail[q] = w[3];
+      } else { /* 26 / 34-byte records alternate between 0 and 2 mod 4: five words and funnel shifts */
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (off & ~3u));
+        const uint32_t sh = (off & 3u) * 8u;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        X[q] = (int32_t)__funnelshift_r(w0, w1, sh), Y[q] = (int32_t)__funnelshift_r(w1, w2, sh), Z[q] = (int32_t)__funnelshift_r(w2, w3, sh);
+        tail[q] = __funnelshift_r(w3, w4, sh);
+      }
+    }
+  }
+  uint32_t tile[kFastPer];
+  bool ok[kFastPer];
+#pragma unroll
+  for (int q = 0; q < kFastPer; ++q) {
+    /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double; main.cpp:200-209 as in the generic kernel */
+    const double rx_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)X[q] ^ 0x80000000u)), bias);
+    const double ry_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)Y[q] ^ 0x80000000u)), bias);
+    const double rz_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)Z[q] ^ 0x80000000u)), bias);
+    const double gx = __dadd_rn(__dmul_rn(rx_, p.sp.scale[0]), p.sp.offset[0]);
+    const double gy = __dadd_rn(__dmul_rn(ry_, p.sp.scale[1]), p.sp.offset[1]);
+    const double gz = __dadd_rn(__dmul_rn(rz_, p.sp.scale[2]), p.sp.offset[2]);
+    const float fX = __fmul_rn(__double2float_rn(__dsub_rn(gx, p.sp.mn[0])), p.sp.rcell[0]); /* :200, x / 2^k == x * 2^-k */
+    const float fY = __fmul_rn(__double2float_rn(__dsub_rn(gy, p.sp.mn[1])), p.sp.rcell[1]); /* :201 */
+    const float fZ = __fmul_rn(__double2float_rn(__dsub_rn(gz, p.sp.mn[2])), p.sp.rcell[2]); /* :202 */
+    const float tx = __fsub_rn(fX, p.sp.origin[0]), ty = __fsub_rn(fY, p.sp.origin[1]);      /* :205-206 */
+    const bool inside = tx >= 0.0f && tx < r0f && ty >= 0.0f && ty < r0f;                    /* :209 */
+    /* the colour is written before the height test (main.cpp:223-224 precede :229): with keys, points below the floor still
+     * travel, carrying +0.0f (a no-op for the height) */
+    ok[q] = inside && ((tail[q] >> 24) & 0x1fu) != 7u && (KEYS || fZ >= 0.0f);
+    /* floor(t) from the significand of t + 2^23 rounded down; garbage (never used) when the point is rejected */
+    const uint32_t cx = __float_as_uint(__fadd_rd(tx, 8388608.0f)) & 0x7fffffu;
+    const uint32_t cy = __float_as_uint(__fadd_rd(ty, 8388608.0f)) & 0x7fffffu;
+    cell[q] = cx + cy * (uint32_t)p.sp.res0;
+    hb[q] = fZ >= 0.0f ? __float_as_uint(fZ) : 0u;
+    tile[q] = ok[q] ? (cy >> p.tile_shift) * (uint32_t)p.tiles_x + (cx >> p.tile_shift) : 0u;
+    if (KEYS) {
+      rgb[q] = 0;
+      if (ok[q] && p.sp.rgb_off >= 0) { /* three u16, 2-byte aligned in every LAS 1.2 format */
+        const uint32_t off = (uint32_t)(q * kFastThreads + (int)threadIdx.x) * (uint32_t)p.record_len;
+        const uint16_t* c16 = reinterpret_cast<const uint16_t*>(stage + off + (uint32_t)p.sp.rgb_off);
+        rgb[q] = (color16(c16[0]) << 16) | (color16(c16[1]) << 8) | color16(c16[2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kFastPer; ++q) {
+    uint32_t rank = 0;
+    if (ok[q]) rank = atomicAdd(&hist[tile[q]], 1u); /* rank < 2048 */
+    slot[q] = ok[q] ? (tile[q] << 16) | rank : 0xffffffffu;
+  }
+}
+
+template <bool KEYS, bool ALIGNED>
+__global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __grid_constant__ BinParams p) {
+  typedef typename PairOf<KEYS>::type Pair;
+  extern __shared__ __align__(128) uint8_t rx_smem[];
+  uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + kFastFill);  /* entries used in this CTA's slice of each bucket (persistent) */
+  uint32_t* hist2 = reinterpret_cast<uint32_t*>(rx_smem + kFastHist); /* points of this step per tile, buffer k & 1 */
+  uint2* offd = reinterpret_cast<uint2*>(rx_smem + kFastOffd);        /* x: first sorted slot of the tile, y: first destination or ~0u */
+  uint32_t* sdest = reinterpret_cast<uint32_t*>(rx_smem + kFastSdest);
+  Pair* spair = reinterpret_cast<Pair*>(rx_smem + kFastSpair);
+  const uint32_t stage_bytes = ((uint32_t)kFastChunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(rx_smem);
+  const uint32_t stage0_s = bar0 + fast_stage0<KEYS>();
+  __shared__ uint32_t total_s;
+
+  const uint32_t n_slices = gridDim.x;
+  if (threadIdx.x < kMaxTiles) {
+    const int t = threadIdx.x;
+    fill[t] = (p.accumulate && t < p.n_tiles) ? p.counts[(size_t)t * n_slices + blockIdx.x] : 0u;
+    hist2[t] = 0;
+    hist2[kMaxTiles + t] = 0;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t n_chunks = (p.n + kFastChunk - 1) / kFastChunk;
+  const int tiles_padded = (p.n_tiles + 31) & ~31; /* whole warps of phase B */
+  auto issue = [&](int64_t c, int s) { /* as in the generic kernel */
+    const int64_t first = c * kFastChunk;
+    const int64_t remaining = p.n - first;
+    const uint32_t count = remaining < kFastChunk ? (uint32_t)remaining : (uint32_t)kFastChunk;
+    const uint32_t bytes = count * (uint32_t)p.record_len, bulk = bytes & ~15u;
+    const uint8_t* src = p.records + first * p.record_len;
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (bulk) {
+        mbar_expect_tx(bar0 + 8 * s, bulk);
+        tma_load_1d(stage0_s + (uint32_t)s * stage_bytes, src, bulk, bar0 + 8 * s);
+      } else {
+        mbar_arrive(bar0 + 8 * s);
+      }
+    }
+    if (threadIdx.x < bytes - bulk) rx_smem[fast_stage0<KEYS>() + (size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
+  };
+
+  int64_t c = (blockIdx.x + gridDim.x - p.cta_rot % gridDim.x) % gridDim.x; /* slices stay indexed by blockIdx.x */
+  if (c < n_chunks) issue(c, 0);
+  __syncthreads();
+  for (int k = 0; c < n_chunks; ++k, c += gridDim.x) {
+    const int s = k & 1;
+    if (c + gridDim.x < n_chunks) issue(c + gridDim.x, s ^ 1);
+    mbar_wait(bar0 + 8 * s, (uint32_t)(k >> 1) & 1u);
+    const uint8_t* stage = rx_smem + fast_stage0<KEYS>() + (size_t)s * stage_bytes;
+    const int64_t remaining = p.n - c * kFastChunk;
+    const int count = remaining < kFastChunk ? (int)remaining : kFastChunk;
+    uint32_t* hist = hist2 + s * kMaxTiles;
+
+    /* A: decode, rank inside the tile */
+    uint32_t cell[kFastPer], hb[kFastPer], slot[kFastPer], rgb[kFastPer];
+    if (count == kFastChunk)
+      fast_decode<KEYS, ALIGNED, true>(p, stage, count, hist, cell, hb, slot, rgb);
+    else
+      fast_decode<KEYS, ALIGNED, false>(p, stage, count, hist, cell, hb, slot, rgb);
+    __syncthreads();
+    /* B: thread t of the first eight warps owns tile t.  Its warp sums, lane by lane, the counts of the tiles of all earlier
+     * groups of 32 (a butterfly turns that into the group's base) and scans its own 32 counts: no second barrier, no
+     * single-warp prefix while fifteen warps wait. */
+    if ((int)threadIdx.x < tiles_padded) {
+      const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, t = threadIdx.x;
+      const uint32_t mine = hist[t];
+      uint32_t before = 0;
+#pragma unroll
+      for (int g = 0; g < kMaxTiles / 32 - 1; ++g)
+        if ((uint32_t)g < w) before += hist[g * 32 + lane];
+      uint32_t incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+        before += __shfl_xor_sync(0xffffffffu, before, d);
+      }
+      uint32_t d0 = 0xffffffffu; /* slice full: this step's points of the tile take the overflow route */
+      if ((int)t < p.n_tiles) {
+        const uint32_t f = fill[t];
+        if (f + mine <= p.slice_cap) {
+          d0 = (uint32_t)(((size_t)t * n_slices + blockIdx.x) * p.slice_cap + f); /* < 2^32: checked by the launcher */
+          fill[t] = f + mine;
+        }
+      }
+      offd[t] = make_uint2(before + incl - mine, d0);
+      hist2[(s ^ 1) * kMaxTiles + t] = 0; /* the other buffer: last read in the previous step, next used in the next */
+      if ((int)t == tiles_padded - 1) total_s = before + incl;
+    }
+    __syncthreads();
+    /* C: scatter into sorted order (shared memory); the four table loads first, then the stores */
+    uint2 od[kFastPer];
+#pragma unroll
+    for (int q = 0; q < kFastPer; ++q) od[q] = offd[slot[q] == 0xffffffffu ? 0u : slot[q] >> 16];
+#pragma unroll
+    for (int q = 0; q < kFastPer; ++q) {
+      if (slot[q] == 0xffffffffu) continue;
+      const uint32_t rank = slot[q] & 0xffffu;
+      const uint32_t j = od[q].x + rank;
+      store_pair(spair + j, cell[q], hb[q], KEYS ? rgb[q] : 0u, p.first_index + c * kFastChunk + (int64_t)(q * kFastThreads + (int)threadIdx.x));
+      sdest[j] = od[q].y == 0xffffffffu ? od[q].y : od[q].y + rank;
+    }
+    __syncthreads();
+    /* D: write out; consecutive lanes hit consecutive addresses inside a tile's run */
+    const uint32_t total = total_s;
+    uint32_t dropped = 0;
+    for (uint32_t j = threadIdx.x; j < total; j += kFastThreads) {
+      const uint32_t d = sdest[j];
+      const Pair v = spair[j];
+      if (d != 0xffffffffu)
+        static_cast<Pair*>(p.pairs)[d] = v;
+      else if (p.finest)
+        apply_pair(p.finest, p.keys, v);
+      else
+        ++dropped;
+    }
+    if (dropped) atomicAdd(p.overflow, dropped);
+    /* no barrier here: what D reads (sdest, spair, total_s) is next written behind the two barriers of the following step,
+     * and the stage the next iteration refills was last read in A, two barriers ago */
+  }
+  for (int t = threadIdx.x; t < p.n_tiles; t += kFastThreads) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
 }
 
 /* Pass 2.  The buckets of the owned tiles, read from every rank's region (own entry = local memory, the others = peer
@@ -430,9 +653,9 @@ struct BinGeometry {
 };
 
 /* development knobs (benchmarks/raster_probe.py); 0 = the built-in choice */
-static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_apply_slices = 0;
+static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_apply_slices = 0, g_knob_bin_generic = 0;
 
-static int bin_geometry(int record_len, bool keys, BinGeometry& g) {
+static int bin_geometry(int record_len, bool keys, const ScatterParams& sp, BinGeometry& g) {
   /* 512 threads x 4 records = steps of 2048 points (runs of ~8 pairs per tile): measured best of {256, 512} x {2, 4, 8}
    * (profiles/raw_r02/raster_probe_*.json) */
   g.threads = g_knob_bin_threads ? g_knob_bin_threads : 512;
@@ -440,14 +663,25 @@ static int bin_geometry(int record_len, bool keys, BinGeometry& g) {
   if (g.threads * g.per > 4096) g.per = 4096 / g.threads;
   g.fn = keys ? (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, true>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, true>))
               : (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, false>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, false>));
-  for (;;) {
-    g.chunk = g.threads * g.per;
-    const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
-    if (g.smem <= 220 * 1024 || g.per == 1) break;
-    g.per >>= 1; /* long records: smaller steps */
+  const size_t fast_stage = ((size_t)kFastChunk * record_len + 16 + 127) & ~(size_t)127;
+  const size_t fast_smem = (keys ? fast_stage0<true>() : fast_stage0<false>()) + 2 * fast_stage;
+  if (g_knob_bin_generic != 1 && g.threads == kFastThreads && g.per == kFastPer && sp.rcell[0] != 0.0f && sp.rcell[1] != 0.0f && sp.rcell[2] != 0.0f &&
+      fast_smem <= 220 * 1024) {
+    const bool aligned = (record_len & 3) == 0;
+    g.fn = keys ? (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, true>) : reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, false>))
+                : (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, true>) : reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, false>));
+    g.chunk = kFastChunk;
+    g.smem = fast_smem;
+  } else {
+    for (;;) {
+      g.chunk = g.threads * g.per;
+      const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
+      g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
+      if (g.smem <= 220 * 1024 || g.per == 1) break;
+      g.per >>= 1; /* long records: smaller steps */
+    }
+    if (g.smem > 220 * 1024) return HMRT_E_ARG;
   }
-  if (g.smem > 220 * 1024) return HMRT_E_ARG;
   HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));
   if (g.ctas_per_sm < 1) return HMRT_E_ARG;
@@ -461,17 +695,18 @@ static int launch_bin(const BinGeometry& g, const BinParams& bp, unsigned grid, 
 
 static int64_t slice_capacity(int64_t points, int n_tiles, int n_slices) {
   int64_t cap = 2 * ((points + (int64_t)n_tiles * n_slices - 1) / ((int64_t)n_tiles * n_slices));
-  cap = (cap + 3) / 4 * 4; /* keep slices 32-byte aligned */
-  return cap < 64 ? 64 : cap;
+  const int64_t floor_cap = 16384 / n_tiles < 64 ? 64 : 16384 / n_tiles; /* small inputs: a step can put 2048 / n_tiles points and more into one slice */
+  if (cap < floor_cap) cap = floor_cap;
+  return (cap + 3) / 4 * 4; /* keep slices 32-byte aligned */
 }
 
 int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int record_len, const ScatterParams& sp, int* finest,
                           unsigned long long* keys, int64_t first_index) {
   BinGeometry bg;
-  int rc = bin_geometry(record_len, keys != nullptr, bg);
+  int rc = bin_geometry(record_len, keys != nullptr, sp, bg);
   const size_t pair_size = keys ? sizeof(uint4) : sizeof(uint2);
   if (rc) return rc;
-  const int tile_shift = binned_tile_shift(sp.res0);
+  const int tile_shift = binned_tile_shift(sp.res0, 1);
   const int tiles_x = (sp.res0 + (1 << tile_shift) - 1) >> tile_shift;
   const int n_tiles = tiles_x * tiles_x;
   /* sub-batches bound the workspace (~16 B per point at 2x mean slice capacity) to ~16 GB */
@@ -510,6 +745,7 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     bp.finest = finest;
     bp.overflow = nullptr;
     bp.accumulate = 0;
+    bp.cta_rot = 0;
     HMRT_CUDA((cudaError_t)launch_bin(bg, bp, (unsigned)n_slices, ctx->stream));
     HMRT_LAUNCHED(ctx);
     ApplyParams ap;
@@ -553,6 +789,7 @@ struct hmrt_rx {
   uint8_t* peer[hmrt::kMaxPeers];
   bool connected;
   bool binned_any;
+  uint32_t chunk_cursor; /* chunks binned since hmrt_rx_begin, modulo n_slices */
   uint32_t epoch;
   int band_row0[hmrt::kMaxPeers + 1];
   int tile_row0[hmrt::kMaxPeers + 1];
@@ -568,6 +805,7 @@ int hmrt_debug_raster_knob(int key, int value) {
   if (key == 0 && (value == 0 || value == 256 || value == 512)) hmrt::g_knob_bin_threads = value;
   else if (key == 1 && value >= 0 && value <= 8) hmrt::g_knob_bin_per = value;
   else if (key == 2 && value >= 0 && value <= 64) hmrt::g_knob_apply_slices = value;
+  else if (key == 3 && value >= 0 && value <= 1) hmrt::g_knob_bin_generic = value;
   else return HMRT_E_ARG;
   return 0;
 }
@@ -579,7 +817,7 @@ int hmrt_rx_create(hmrt_ctx* ctx, int coarse_res, int levels, int rank, int worl
   int64_t idx[HMRT_MAX_LEVELS];
   int rc = hmrt::pyramid_layout(coarse_res, levels, res, idx, nullptr);
   if (rc) return rc;
-  const int shift = hmrt::binned_tile_shift(res[0]);
+  const int shift = hmrt::binned_tile_shift(res[0], world);
   /* bands are whole tile rows and must be whole 128-row mip tiles; the fused mip kernel covers 8 levels */
   if (res[0] % 128 != 0 || shift < 7 || levels > 8 || levels < 2) return HMRT_E_SHAPE;
   /* the fused gather + mip kernel moves 16-byte pieces of level 0 and 8-byte pieces of level 1: odd coarse resolutions put
@@ -684,6 +922,7 @@ int hmrt_rx_begin(hmrt_rx* rx) {
   HMRT_CUDA(cudaMemsetAsync(rx->region + offsetof(hmrt::RxHeader, overflow), 0, sizeof(uint32_t), st));
   if (band_rows) HMRT_CUDA(cudaMemsetAsync(rx->region + rx->band_off, 0, band_rows * (size_t)rx->res0 * sizeof(float), st));
   rx->binned_any = false;
+  rx->chunk_cursor = 0;
   return 0;
 }
 
@@ -695,10 +934,10 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   if (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15)) return HMRT_E_ARG;
   hmrt::DeviceGuard guard(rx->ctx->device);
   hmrt::BinGeometry bg;
-  int rc = hmrt::bin_geometry(record_len, false, bg);
-  if (rc) return rc;
   hmrt::BinParams bp;
-  rc = hmrt::fill_scatter_params(xf, rx->res0, bp.sp);
+  int rc = hmrt::fill_scatter_params(xf, rx->res0, bp.sp);
+  if (rc) return rc;
+  rc = hmrt::bin_geometry(record_len, false, bp.sp, bg);
   if (rc) return rc;
   bp.sp.cls_off = 15;
   bp.sp.rgb_off = hmrt::kLasRgbOff[point_format];
@@ -717,6 +956,8 @@ int hmrt_rx_bin(hmrt_rx* rx, const uint8_t* d_records, int64_t n, int record_len
   bp.finest = nullptr;
   bp.overflow = reinterpret_cast<uint32_t*>(rx->region + offsetof(hmrt::RxHeader, overflow));
   bp.accumulate = rx->binned_any ? 1 : 0;
+  bp.cta_rot = rx->chunk_cursor;
+  rx->chunk_cursor = (uint32_t)((rx->chunk_cursor + (n + bg.chunk - 1) / bg.chunk) % rx->n_slices);
   /* always n_slices CTAs: the slice layout is part of the exchange geometry */
   HMRT_CUDA((cudaError_t)hmrt::launch_bin(bg, bp, (unsigned)rx->n_slices, rx->ctx->stream));
   HMRT_LAUNCHED(rx->ctx);

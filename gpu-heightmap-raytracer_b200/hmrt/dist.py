@@ -150,10 +150,14 @@ class SharedFrames:
 
 def band_rows(res0: int, world_size: int):
     """rows[r] .. rows[r + 1] = the finest-level rows rank r owns in the peer-memory exchange: whole rows of grid tiles
-    (16 x 16 tiles, csrc/rasterx.cu), dealt out contiguously and as evenly as possible -- the host-side mirror of
+    (ceil(res0 / 2048) tiles per axis, at least 8, at most 16; 16 when the world size does not divide 8 --
+    binned_tile_shift, csrc/rasterx.cu), dealt out contiguously and as evenly as possible -- the host-side mirror of
     hmrt_rx_bands (tests/test_dist_gloo.py compares the two)."""
+    per_axis = min(16, max(8, (res0 + 2047) // 2048))
+    if 8 % world_size != 0:
+        per_axis = 16
     shift = 0
-    while ((res0 + (1 << shift) - 1) >> shift) > 16:
+    while ((res0 + (1 << shift) - 1) >> shift) > per_axis:
         shift += 1
     tile = 1 << shift
     tiles = (res0 + tile - 1) >> shift

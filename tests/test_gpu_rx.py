@@ -170,6 +170,19 @@ def test_rx_shape_checks(cuda_ctx):
     from hmrt import dist as hd
     assert hd.band_rows(2048, 1) == [0, 2048]
     assert lib.hmrt_rx_destroy(rx) == 0
+    # the Python mirror of the band split agrees with the library for every world size (tile rows: 8 per axis when the
+    # world size divides 8, else 16)
+    for coarse, levels in ((16, 8), (32, 8), (24, 8), (128, 8)):
+        for world in (1, 2, 3, 4, 5, 8, 16):
+            rx = C.c_void_p()
+            rc = lib.hmrt_rx_create(cuda_ctx._h, coarse, levels, 0, world, 1000, C.byref(rx))
+            if rc != 0:
+                assert rc == -3  # tile rows smaller than a mip tile
+                continue
+            rows = (C.c_int * (world + 1))()
+            assert lib.hmrt_rx_bands(rx, rows) == 0
+            assert list(rows) == hd.band_rows(coarse << (levels - 1), world), (coarse, levels, world)
+            assert lib.hmrt_rx_destroy(rx) == 0
 
 
 def test_raster_pipeline_single_modes_agree(cuda_ctx):
