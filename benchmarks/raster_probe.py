@@ -49,7 +49,7 @@ def main():
     ctx.set_scatter_mode(0)
     for v in [v for v in args.variants.split(",") if v]:
         th, per, sl, generic = ([int(x) for x in v.split(":")] + [0])[:4]
-        for key, val in ((0, th), (1, per), (2, sl), (3, generic)):
+        for key, val in ((0, th), (1, per), (3, generic)):
             assert ctx.lib.hmrt_debug_raster_knob(key, val) == 0
         rp = hd.RasterPipeline(ctx, rpl.COARSE, rpl.LEVELS, single=True, force_mode="peer")
         best = None
@@ -60,7 +60,7 @@ def main():
         out["variant_" + v] = {**best, "total_ms": sum(best.values())}
         hashes["variant_" + v] = rpl.finest_hash(torch, pyr[idx[0]:])
         rp.close()
-    for key in (0, 1, 2, 3):
+    for key in (0, 1, 3):
         ctx.lib.hmrt_debug_raster_knob(key, 0)
     out["hashes_equal"] = len(set(hashes.values())) == 1
     print(json.dumps(out))

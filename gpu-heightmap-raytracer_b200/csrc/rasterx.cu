@@ -318,12 +318,12 @@ __global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__
  *     aligned-up pointers made the sorted pairs generic LD / ST).
  * Shared memory: [2 mbarriers][fill 256][hist 2 x 256][offs, dest0 256 x 2][sdest 2048][spair 2048][stage 0][stage 1].
  */
-constexpr int kFastThreads = 512, kFastPer = 4, kFastChunk = kFastThreads * kFastPer;
-constexpr uint32_t kFastFill = 16, kFastHist = kFastFill + 4 * kMaxTiles, kFastOffd = kFastHist + 8 * kMaxTiles,
-                   kFastSdest = kFastOffd + 8 * kMaxTiles, kFastSpair = kFastSdest + 4 * kFastChunk;
-template <bool KEYS> __host__ __device__ constexpr uint32_t fast_stage0() { return (kFastSpair + (uint32_t)sizeof(typename PairOf<KEYS>::type) * kFastChunk + 127u) & ~127u; }
+constexpr uint32_t kFastFill = 16, kFastHist = kFastFill + 4 * kMaxTiles, kFastOffd = kFastHist + 8 * kMaxTiles, kFastSdest = kFastOffd + 8 * kMaxTiles;
+template <bool KEYS, int CHUNK> __host__ __device__ constexpr uint32_t fast_stage0() {
+  return (kFastSdest + 4u * CHUNK + (uint32_t)sizeof(typename PairOf<KEYS>::type) * CHUNK + 127u) & ~127u;
+}
 
-template <bool KEYS, bool ALIGNED, bool FULL>
+template <bool KEYS, bool ALIGNED, bool FULL, int kFastThreads, int kFastPer>
 __device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* stage, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
                                             uint32_t (&hb)[kFastPer], uint32_t (&slot)[kFastPer], uint32_t (&rgb)[kFastPer]) {
   const float r0f = (float)p.sp.res0;
@@ -392,9 +392,12 @@ __device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* s
   }
 }
 
-template <bool KEYS, bool ALIGNED>
-__global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __grid_constant__ BinParams p) {
+template <bool KEYS, bool ALIGNED, int kFastThreads, int kFastPer, int MIN_CTAS>
+__global__ void __launch_bounds__(kFastThreads, MIN_CTAS) rx_bin_fast_kernel(const __grid_constant__ BinParams p) {
   typedef typename PairOf<KEYS>::type Pair;
+  constexpr int kFastChunk = kFastThreads * kFastPer;
+  constexpr uint32_t kFastSpair = kFastSdest + 4 * kFastChunk;
+  static_assert(kFastThreads >= kMaxTiles, "phase B: one thread per tile");
   extern __shared__ __align__(128) uint8_t rx_smem[];
   uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + kFastFill);  /* entries used in this CTA's slice of each bucket (persistent) */
   uint32_t* hist2 = reinterpret_cast<uint32_t*>(rx_smem + kFastHist); /* points of this step per tile, buffer k & 1 */
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __gr
   Pair* spair = reinterpret_cast<Pair*>(rx_smem + kFastSpair);
   const uint32_t stage_bytes = ((uint32_t)kFastChunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(rx_smem);
-  const uint32_t stage0_s = bar0 + fast_stage0<KEYS>();
+  const uint32_t stage0_s = bar0 + fast_stage0<KEYS, kFastChunk>();
   __shared__ uint32_t total_s;
 
   const uint32_t n_slices = gridDim.x;
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __gr
         mbar_arrive(bar0 + 8 * s);
       }
     }
-    if (threadIdx.x < bytes - bulk) rx_smem[fast_stage0<KEYS>() + (size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
+    if (threadIdx.x < bytes - bulk) rx_smem[fast_stage0<KEYS, kFastChunk>() + (size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
   };
 
   int64_t c = (blockIdx.x + gridDim.x - p.cta_rot % gridDim.x) % gridDim.x; /* slices stay indexed by blockIdx.x */
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __gr
     const int s = k & 1;
     if (c + gridDim.x < n_chunks) issue(c + gridDim.x, s ^ 1);
     mbar_wait(bar0 + 8 * s, (uint32_t)(k >> 1) & 1u);
-    const uint8_t* stage = rx_smem + fast_stage0<KEYS>() + (size_t)s * stage_bytes;
+    const uint8_t* stage = rx_smem + fast_stage0<KEYS, kFastChunk>() + (size_t)s * stage_bytes;
     const int64_t remaining = p.n - c * kFastChunk;
     const int count = remaining < kFastChunk ? (int)remaining : kFastChunk;
     uint32_t* hist = hist2 + s * kMaxTiles;
@@ -455,9 +458,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) rx_bin_fast_kernel(const __gr
     /* A: decode, rank inside the tile */
     uint32_t cell[kFastPer], hb[kFastPer], slot[kFastPer], rgb[kFastPer];
     if (count == kFastChunk)
-      fast_decode<KEYS, ALIGNED, true>(p, stage, count, hist, cell, hb, slot, rgb);
+      fast_decode<KEYS, ALIGNED, true, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
     else
-      fast_decode<KEYS, ALIGNED, false>(p, stage, count, hist, cell, hb, slot, rgb);
+      fast_decode<KEYS, ALIGNED, false, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
     __syncthreads();
     /* B: thread t of the first eight warps owns tile t.  Its warp sums, lane by lane, the counts of the tiles of all earlier
      * groups of 32 (a butterfly turns that into the group's base) and scans its own 32 counts: no second barrier, no
@@ -653,35 +656,47 @@ struct BinGeometry {
 };
 
 /* development knobs (benchmarks/raster_probe.py); 0 = the built-in choice */
-static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_apply_slices = 0, g_knob_bin_generic = 0;
+static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_bin_generic = 0;
 
 static int bin_geometry(int record_len, bool keys, const ScatterParams& sp, BinGeometry& g) {
-  /* 512 threads x 4 records = steps of 2048 points (runs of ~8 pairs per tile): measured best of {256, 512} x {2, 4, 8}
-   * (profiles/raw_r02/raster_probe_*.json) */
+  /* The specialised kernel: 256 threads x 8 records = steps of 2048 points, two CTAs per SM (measured best of 512 x 4, 512 x 2,
+   * 256 x 4, 256 x 8: 2.69 / 3.25 / 2.98 / 2.58 ms for 500 M points, profiles/raw_r02/raster_bin_step_geometry.json); records so
+   * long that two CTAs no longer fit take 256 x 4.  Anything else (a cell size that is not a power of two, the development
+   * knobs) runs the generic kernel. */
+  const bool fast_ok = !g_knob_bin_generic && !g_knob_bin_threads && !g_knob_bin_per && sp.rcell[0] != 0.0f && sp.rcell[1] != 0.0f && sp.rcell[2] != 0.0f;
+  const bool aligned = (record_len & 3) == 0;
+  if (fast_ok) {
+#define HMRT_FAST_CASE(T, P, M)                                                                                                          \
+  {                                                                                                                                      \
+    const size_t smem = (keys ? fast_stage0<true, T * P>() : fast_stage0<false, T * P>()) + 2 * (((size_t)T * P * record_len + 16 + 127) & ~(size_t)127); \
+    if (smem <= 112 * 1024) {                                                                                                            \
+      g.fn = keys ? (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, true, T, P, M>)                                   \
+                             : reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, false, T, P, M>))                                 \
+                  : (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, true, T, P, M>)                                  \
+                             : reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, false, T, P, M>));                               \
+      g.threads = T, g.per = P, g.chunk = T * P, g.smem = smem;                                                                          \
+      HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));                                   \
+      HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));                                 \
+      if (g.ctas_per_sm >= 2) return 0;                                                                                                  \
+    }                                                                                                                                    \
+  }
+    HMRT_FAST_CASE(256, 8, 2)
+    HMRT_FAST_CASE(256, 4, 2)
+#undef HMRT_FAST_CASE
+  }
   g.threads = g_knob_bin_threads ? g_knob_bin_threads : 512;
   g.per = g_knob_bin_per ? g_knob_bin_per : 4;
   if (g.threads * g.per > 4096) g.per = 4096 / g.threads;
   g.fn = keys ? (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, true>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, true>))
               : (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, false>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, false>));
-  const size_t fast_stage = ((size_t)kFastChunk * record_len + 16 + 127) & ~(size_t)127;
-  const size_t fast_smem = (keys ? fast_stage0<true>() : fast_stage0<false>()) + 2 * fast_stage;
-  if (g_knob_bin_generic != 1 && g.threads == kFastThreads && g.per == kFastPer && sp.rcell[0] != 0.0f && sp.rcell[1] != 0.0f && sp.rcell[2] != 0.0f &&
-      fast_smem <= 220 * 1024) {
-    const bool aligned = (record_len & 3) == 0;
-    g.fn = keys ? (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, true>) : reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, false>))
-                : (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, true>) : reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, false>));
-    g.chunk = kFastChunk;
-    g.smem = fast_smem;
-  } else {
-    for (;;) {
-      g.chunk = g.threads * g.per;
-      const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-      g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
-      if (g.smem <= 220 * 1024 || g.per == 1) break;
-      g.per >>= 1; /* long records: smaller steps */
-    }
-    if (g.smem > 220 * 1024) return HMRT_E_ARG;
+  for (;;) {
+    g.chunk = g.threads * g.per;
+    const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
+    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
+    if (g.smem <= 220 * 1024 || g.per == 1) break;
+    g.per >>= 1; /* long records: smaller steps */
   }
+  if (g.smem > 220 * 1024) return HMRT_E_ARG;
   HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));
   if (g.ctas_per_sm < 1) return HMRT_E_ARG;
@@ -800,11 +815,11 @@ extern "C" {
 int hmrt_rx_barrier(hmrt_rx* rx);
 
 /* Development knobs of the binned rasterisation (not part of include/hmrt.h): key 0 = CTA size of the bin pass (256 / 512),
- * 1 = records per thread and step, 2 = slices per CTA of the apply pass; value 0 restores the built-in choice. */
+ * 1 = records per thread and step (either one selects the generic bin kernel), 3 = 1: the generic bin kernel; value 0 restores the
+ * built-in choice. */
 int hmrt_debug_raster_knob(int key, int value) {
   if (key == 0 && (value == 0 || value == 256 || value == 512)) hmrt::g_knob_bin_threads = value;
   else if (key == 1 && value >= 0 && value <= 8) hmrt::g_knob_bin_per = value;
-  else if (key == 2 && value >= 0 && value <= 64) hmrt::g_knob_apply_slices = value;
   else if (key == 3 && value >= 0 && value <= 1) hmrt::g_knob_bin_generic = value;
   else return HMRT_E_ARG;
   return 0;
