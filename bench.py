@@ -518,26 +518,57 @@ def _run_gpu_arm(args):
                         "walk issues no load for air-phase iterations and most of the rest hits L1/L2, so the kernel is issue/FMA-bound, not bandwidth-bound "
                         "(see `binding` and DESIGN.md section 4.1)"}
 
-    # ---- e2e: host buffers through the C ABI (hmrt_trace_host): camera H2D + framebuffer D2H in the timed region
-    host_fb = torch.empty((POSES, rows, W, 3), dtype=torch.uint8).pin_memory()
+    # ---- e2e: host buffers through the C ABI: camera H2D + framebuffer D2H in the timed region.  The way a double-buffered
+    # renderer calls it: hmrt_trace_host_begin(step s + 1) before hmrt_trace_host_wait(step s), two pinned host frame buffers,
+    # so the traversal of one step runs under the device->host copies of the previous one.  Every step's frames are complete in
+    # host memory inside the timed region.  The one-call-at-a-time form (hmrt_trace_host) is timed next to it.
+    host_fbs = [torch.empty((POSES, rows, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     for s in range(min(2, Wu)):
-        ctx.trace_host(W, H, cams_by_step[s], opts, host_fb)
+        ctx.trace_host(W, H, cams_by_step[s], opts, host_fbs[s & 1])
     e2e_repeats = max(1, min(repeats, int(math.ceil(args.min_seconds / max(1e-3, K * (ms / steps_timed) * 1e-3 * 1.1)))))
-    run.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_repeats):
-        for cams in timed_batches:
-            ctx.trace_host(W, H, cams, opts, host_fb)
+
+    def e2e_loop(pipelined):
+        run.barrier()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(e2e_repeats):
+            for cams in timed_batches:
+                if pipelined:
+                    ctx.trace_host_begin(W, H, cams, opts, host_fbs[n & 1])
+                    if n:
+                        ctx.trace_host_wait()
+                else:
+                    ctx.trace_host(W, H, cams, opts, host_fbs[n & 1])
+                n += 1
+        if pipelined:
+            ctx.trace_host_wait()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec, n
+
+    sync_s, n_calls = e2e_loop(False)
+    e2e_s, n_calls = e2e_loop(True)
+    # the frames of the last step, as delivered to host memory, equal a device-side render of the same cameras
+    ctx.trace(W, H, timed_batches[-1], opts, out=fbs[0])
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    host_ok = bool(torch.equal(host_fbs[(n_calls - 1) & 1].cuda(), fbs[0]))
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        t = torch.tensor([1 if host_ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        host_ok = bool(t.item())
     e2e = {"value": rays_per_step * K * e2e_repeats / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": POSES * 36,
            "d2h_bytes_per_step": POSES * W * H * 3, "ms_per_step": 1e3 * e2e_s / (K * e2e_repeats), "steps_timed": K * e2e_repeats,
-           "note": "hmrt_trace_host: per-step cameras from host memory (36 B each, sent with the launch) + whole-job RGB8 framebuffers D2H into pinned host memory; "
-                   "one persistent launch per step, every quarter-frame row segment is copied the moment its last tile is stored (stream memory operation on the copy stream); heightmap resident"}
+           "host_frames_equal_device": host_ok,
+           "one_call_at_a_time": {"value": rays_per_step * K * e2e_repeats / sync_s / 1e6, "ms_per_step": 1e3 * sync_s / (K * e2e_repeats),
+                                  "what": "hmrt_trace_host (synchronous: returns with the step's frames in host memory), one pinned host buffer pair as above"},
+           "note": "hmrt_trace_host_begin / hmrt_trace_host_wait, two calls in flight (double-buffered renderer): per-step cameras from host memory "
+                   "(36 B each, sent with the launches) + whole-job RGB8 framebuffers D2H into two alternating pinned host buffers; inside a call one lean "
+                   "launch per frame on alternating streams, each followed by its device->host copy on a copy stream; the traversal of step s + 1 runs "
+                   "under the copies of step s; every step's frames are complete in host memory inside the timed region; heightmap resident"}
 
     # ---- frame assembly on the multi-GPU path (the reference delivers ONE complete frame per call, main.cpp:675-703):
     # every rank stores its row tiles straight into rank 0's frames over NVLink from inside the traversal kernel

@@ -97,6 +97,7 @@ int hmrt_destroy(hmrt_ctx* ctx) {
       cudaStreamDestroy(ctx->frame_stream[i]);
     }
     cudaEventDestroy(ctx->prep_event);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->host_done[i]);
     cudaStreamDestroy(ctx->copy_stream);
   }
   delete ctx;

@@ -53,9 +53,12 @@ struct hmrt_ctx {
   /* per-frame constants for multi-frame launches */
   hmrt::FrameConsts* d_frames;
   int frames_cap;
-  /* context-owned framebuffer for hmrt_trace_host */
+  /* context-owned framebuffers for hmrt_trace_host: kHostCalls halves, one per call in flight */
   uint8_t* d_fb;
   size_t fb_cap;
+  size_t fb_half;                /* bytes per half */
+  unsigned host_begun, host_waited; /* hmrt_trace_host_begin / _wait: calls enqueued / collected */
+  cudaEvent_t host_done[2];      /* recorded on the copy stream behind the last copy of a call */
   /* hmrt_trace_host: frames alternate between two streams, copies run on a third */
   cudaStream_t copy_stream;
   cudaStream_t frame_stream[2];

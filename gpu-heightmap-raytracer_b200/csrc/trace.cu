@@ -604,7 +604,7 @@ __global__ void seg_force_kernel(hmrt::SegDone* sd, int n) {
  * device->host copies therefore trail the traversal by a quarter of a frame instead of a whole launch.
  */
 static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames, const hmrt_trace_opts* opts,
-                               uint8_t* h_rgb, size_t frame_bytes, stream_wait_value32_fn wait_value) {
+                               uint8_t* h_rgb, size_t frame_bytes, stream_wait_value32_fn wait_value, uint8_t* d_fb) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const int n_tiles = (H + HMRT_ROW_TILE - 1) / HMRT_ROW_TILE;
   const int local_tiles = opts->tile_first < n_tiles ? (n_tiles - opts->tile_first + stride - 1) / stride : 0;
@@ -633,7 +633,7 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
   HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->prep_event, 0)); /* the flags are zero before anybody polls them */
   for (int l = 0; l < n_launches; ++l) {
     const int f0 = l * per, nf = n_frames - f0 < per ? n_frames - f0 : per;
-    rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0,
+    rc = hmrt::launch_trace(ctx, ctx->stream, base, l, 0, W, H, h_cameras + f0, nf, opts, d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0,
                             sd + (size_t)f0 * segs, false, segs);
     if (rc) break;
   }
@@ -656,7 +656,7 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
       const int drc = wait_value(ctx->copy_stream, flag, 1u, 0u);
       if (drc != 0) return 999; /* cudaErrorUnknown: the driver refused the stream memory operation */
       const size_t off = (size_t)f * frame_bytes + r0 * row_bytes;
-      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, ctx->d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   return 0;
 }
@@ -664,7 +664,7 @@ static int trace_host_streamed(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h
 /* The launch / copy schedule of hmrt_trace_host; any error leaves through the caller, which drains the internal streams
  * first so that no copy into h_rgb and no kernel writing d_fb is still in flight when the caller sees the error. */
 static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames, const hmrt_trace_opts* opts,
-                              uint8_t* h_rgb, size_t frame_bytes) {
+                              uint8_t* h_rgb, size_t frame_bytes, uint8_t* d_fb) {
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   /*
    * One launch per frame group, alternating between two internal streams so that the tail of launch l
@@ -726,11 +726,11 @@ static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_
       const size_t r0 = (size_t)t0 * HMRT_ROW_TILE, r1 = (size_t)t1 * HMRT_ROW_TILE < rows_total ? (size_t)t1 * HMRT_ROW_TILE : rows_total;
       const size_t off = (size_t)f0 * frame_bytes + r0 * row_bytes;
       cudaStream_t st = ctx->frame_stream[slot & 1];
-      int prc = hmrt::launch_trace(ctx, st, base, slot, f0, W, H, h_cameras + f0, 1, opts, ctx->d_fb + off, nullptr, t0, t1 - t0);
+      int prc = hmrt::launch_trace(ctx, st, base, slot, f0, W, H, h_cameras + f0, 1, opts, d_fb + off, nullptr, t0, t1 - t0);
       if (prc) return prc;
       HMRT_CUDA(cudaEventRecord(ctx->frame_event[slot & 1], st));
       HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[slot & 1], 0));
-      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, ctx->d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      HMRT_CUDA(cudaMemcpyAsync(h_rgb + off, d_fb + off, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
     return 0;
   };
@@ -743,12 +743,12 @@ static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_
     /* the launches alternate between two streams, i.e. each one's drain runs under the next one's head: the lean kernel
      * without the tile-granular tail (see launch_trace), except for the very last whole launch of the call */
     const bool overlapped = l + 1 < whole_end || split_last;
-    rc = hmrt::launch_trace(ctx, st, base, slot, f0, W, H, h_cameras + f0, nf, opts, ctx->d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0, nullptr,
+    rc = hmrt::launch_trace(ctx, st, base, slot, f0, W, H, h_cameras + f0, nf, opts, d_fb + (size_t)f0 * frame_bytes, nullptr, 0, 0, nullptr,
                             overlapped);
     if (rc) return rc;
     HMRT_CUDA(cudaEventRecord(ctx->frame_event[slot & 1], st));
     HMRT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_event[slot & 1], 0));
-    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f0 * frame_bytes, ctx->d_fb + (size_t)f0 * frame_bytes, frame_bytes * (size_t)nf,
+    HMRT_CUDA(cudaMemcpyAsync(h_rgb + (size_t)f0 * frame_bytes, d_fb + (size_t)f0 * frame_bytes, frame_bytes * (size_t)nf,
                               cudaMemcpyDeviceToHost, ctx->copy_stream));
     ++slot;
   }
@@ -759,31 +759,51 @@ static int trace_host_enqueue(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_
   return 0;
 }
 
-int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
-                    const hmrt_trace_opts* opts, uint8_t* h_rgb) {
+/* Everything hmrt_trace_host_begin enqueued -- kernels writing d_fb, copies into the callers' buffers -- has finished. */
+static int trace_host_drain(hmrt_ctx* ctx, bool collect = true) {
+  cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = ctx->copy_stream ? cudaStreamSynchronize(ctx->frame_stream[0]) : cudaSuccess;
+  cudaError_t e1 = ctx->copy_stream ? cudaStreamSynchronize(ctx->frame_stream[1]) : cudaSuccess;
+  cudaError_t e2 = ctx->copy_stream ? cudaStreamSynchronize(ctx->copy_stream) : cudaSuccess;
+  if (collect) ctx->host_waited = ctx->host_begun; /* else: the calls stay "in flight" for their hmrt_trace_host_wait */
+  if (e0 != cudaSuccess) return (int)e0;
+  if (e != cudaSuccess) return (int)e;
+  if (e1 != cudaSuccess) return (int)e1;
+  return (int)e2;
+}
+
+int hmrt_trace_host_begin(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames, const hmrt_trace_opts* opts,
+                          uint8_t* h_rgb) {
   int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
   if (rc) return rc;
   if (!h_rgb || opts->full_frame_output) return HMRT_E_ARG; /* the host copy is always compact */
+  if (ctx->host_begun - ctx->host_waited >= (unsigned)HMRT_MAX_HOST_CALLS_IN_FLIGHT) return HMRT_E_STATE;
   hmrt::DeviceGuard guard(ctx->device);
   const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
   const size_t frame_bytes = (size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W * 3;
   const size_t bytes = frame_bytes * (size_t)n_frames;
-  if (bytes == 0) return 0;
-  if (ctx->fb_cap < bytes) {
-    if (ctx->d_fb) HMRT_CUDA(cudaFree(ctx->d_fb));
-    ctx->d_fb = nullptr;
-    ctx->fb_cap = 0;
-    HMRT_CUDA(cudaMalloc(&ctx->d_fb, bytes));
-    ctx->fb_cap = bytes;
-  }
+  const size_t half = (bytes + 255) & ~(size_t)255;
   if (!ctx->copy_stream) {
     HMRT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       HMRT_CUDA(cudaStreamCreateWithFlags(&ctx->frame_stream[i], cudaStreamNonBlocking));
       HMRT_CUDA(cudaEventCreateWithFlags(&ctx->frame_event[i], cudaEventDisableTiming));
+      HMRT_CUDA(cudaEventCreateWithFlags(&ctx->host_done[i], cudaEventDisableTiming));
     }
     HMRT_CUDA(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
   }
+  if (ctx->fb_half < half) { /* grow: nothing may be running in the old halves (the calls keep their place in the wait order) */
+    rc = trace_host_drain(ctx, false);
+    if (rc) return rc;
+    if (ctx->d_fb) HMRT_CUDA(cudaFree(ctx->d_fb));
+    ctx->d_fb = nullptr;
+    ctx->fb_cap = ctx->fb_half = 0;
+    HMRT_CUDA(cudaMalloc(&ctx->d_fb, half * HMRT_MAX_HOST_CALLS_IN_FLIGHT));
+    ctx->fb_cap = half * HMRT_MAX_HOST_CALLS_IN_FLIGHT;
+    ctx->fb_half = half;
+  }
+  const unsigned call = ctx->host_begun;
+  uint8_t* d_fb = ctx->d_fb + (size_t)(call % HMRT_MAX_HOST_CALLS_IN_FLIGHT) * ctx->fb_half;
   /* Schedules (measured on B200, 4K frames, profiles/raw_r02/trace_host_variants.txt): for a batch of frames the per-group
    * schedule (one lean launch per frame on alternating streams, each followed by its copy) takes 8.83 ms per 16-frame step
    * against 8.00 ms for the traversal alone and 7.13 ms for the copies alone (55.8 GB/s, the Gen5 x16 link); the streamed
@@ -792,21 +812,63 @@ int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, i
    * Variant 0 picks accordingly. */
   const bool streamed = ctx->host_variant == 2 || (ctx->host_variant == 0 && n_frames == 1);
   stream_wait_value32_fn wait_value = streamed ? stream_wait_value32() : nullptr;
-  if (wait_value)
-    rc = trace_host_streamed(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes, wait_value);
-  else
-    rc = trace_host_enqueue(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes);
-  cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
+  if (bytes == 0) {
+    rc = 0; /* a rank that owns no tile of the frame: nothing to enqueue, the call still counts */
+  } else if (wait_value) {
+    /* the segment flags are one set per context: a streamed call starts with nothing else in flight */
+    if (ctx->host_begun != ctx->host_waited) {
+      rc = trace_host_drain(ctx, false);
+      if (rc) return rc;
+    }
+    rc = trace_host_streamed(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes, wait_value, d_fb);
+  } else {
+    rc = trace_host_enqueue(ctx, W, H, h_cameras, n_frames, opts, h_rgb, frame_bytes, d_fb);
+  }
+  if (rc) { /* whatever was enqueued before the failure finishes before the caller sees the error */
+    trace_host_drain(ctx);
+    return rc;
+  }
+  /* every kernel of the call is followed by its copy on the copy stream: one event behind the last copy covers the call */
+  cudaError_t e = cudaEventRecord(ctx->host_done[call % HMRT_MAX_HOST_CALLS_IN_FLIGHT], ctx->copy_stream);
+  if (e != cudaSuccess) {
+    trace_host_drain(ctx);
+    return (int)e;
+  }
+  ctx->host_begun = call + 1;
+  return 0;
+}
+
+int hmrt_trace_host_wait(hmrt_ctx* ctx) {
+  if (!ctx) return HMRT_E_ARG;
+  if (ctx->host_begun == ctx->host_waited) return HMRT_E_STATE;
+  hmrt::DeviceGuard guard(ctx->device);
+  cudaError_t e = cudaEventSynchronize(ctx->host_done[ctx->host_waited % HMRT_MAX_HOST_CALLS_IN_FLIGHT]);
+  ++ctx->host_waited;
+  if (e != cudaSuccess) { /* a failed call poisons the streams: leave nothing in flight */
+    trace_host_drain(ctx);
+    return (int)e;
+  }
+  return 0;
+}
+
+int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
+                    const hmrt_trace_opts* opts, uint8_t* h_rgb) {
+  int rc = hmrt::check_trace_args(ctx, W, H, h_cameras, n_frames, opts);
+  if (rc) return rc;
+  if (!h_rgb || opts->full_frame_output) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  const int stride = opts->tile_stride > 0 ? opts->tile_stride : 1;
+  if ((size_t)hmrt::rows_local(H, opts->tile_first, stride) * (size_t)W * 3 * (size_t)n_frames == 0) return 0;
+  /* the synchronous form collects everything, also calls begun earlier and not yet waited for */
+  if (ctx->host_begun - ctx->host_waited >= (unsigned)HMRT_MAX_HOST_CALLS_IN_FLIGHT) {
+    rc = trace_host_drain(ctx);
+    if (rc) return rc;
+  }
+  rc = hmrt_trace_host_begin(ctx, W, H, h_cameras, n_frames, opts, h_rgb);
   /* one exit: whatever was enqueued -- kernels writing d_fb, copies into h_rgb -- has finished when the caller gets
    * control back, also on the error paths */
-  cudaError_t e = cudaStreamSynchronize(ctx->frame_stream[0]);
-  cudaError_t e1 = cudaStreamSynchronize(ctx->frame_stream[1]);
-  cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
-  if (rc) return rc;
-  if (e0 != cudaSuccess) return (int)e0;
-  if (e != cudaSuccess) return (int)e;
-  if (e1 != cudaSuccess) return (int)e1;
-  return (int)e2;
+  const int drc = trace_host_drain(ctx);
+  return rc ? rc : drc;
 }
 
 /* Development knobs of the traversal launcher (not part of include/hmrt.h): key 0 = tile-granular tail (-1 auto, 0 off,

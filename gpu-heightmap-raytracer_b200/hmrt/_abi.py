@@ -84,6 +84,8 @@ PROTOTYPES = {
     "hmrt_trace_opts_default": (None, [C.POINTER(TraceOpts), C.c_float]),
     "hmrt_trace": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Camera), C.c_int, C.POINTER(TraceOpts), _P, _P]),
     "hmrt_trace_host": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Camera), C.c_int, C.POINTER(TraceOpts), _P]),
+    "hmrt_trace_host_begin": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Camera), C.c_int, C.POINTER(TraceOpts), _P]),
+    "hmrt_trace_host_wait": (C.c_int, [_P]),
     "hmrt_rows_local": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "hmrt_clear_heightmap": (C.c_int, [_P]),
     "hmrt_clear_section": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

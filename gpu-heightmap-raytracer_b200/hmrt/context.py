@@ -215,23 +215,37 @@ class Context:
                                   self._dev(hit_t, torch.int32, "hits") if hit_t is not None else None), "hmrt_trace")
         return out, hit_t
 
+    @staticmethod
+    def _host_ptr(out_host, need: int) -> int:
+        if hasattr(out_host, "data_ptr"):
+            if out_host.is_cuda or out_host.numel() < need or not out_host.is_contiguous():
+                raise ValueError("out_host must be a contiguous CPU uint8 tensor of sufficient size")
+            return out_host.data_ptr()
+        if out_host.nbytes < need:
+            raise ValueError("out_host too small")
+        return out_host.ctypes.data
+
     def trace_host(self, W: int, H: int, cameras, opts: TraceOpts, out_host):
         """Host-buffer variant (hmrt_trace_host): out_host is a (pinned) CPU uint8 tensor/array."""
         cams = _cam_array(cameras)
         n = len(cams)
-        rows = rows_local(H, opts.tile_first, opts.tile_stride)
-        need = n * rows * W * 3
-        if hasattr(out_host, "data_ptr"):
-            if out_host.is_cuda or out_host.numel() < need or not out_host.is_contiguous():
-                raise ValueError("out_host must be a contiguous CPU uint8 tensor of sufficient size")
-            ptr = out_host.data_ptr()
-        else:
-            if out_host.nbytes < need:
-                raise ValueError("out_host too small")
-            ptr = out_host.ctypes.data
+        ptr = self._host_ptr(out_host, n * rows_local(H, opts.tile_first, opts.tile_stride) * W * 3)
         self._bind_stream()
         check(self.lib.hmrt_trace_host(self._h, W, H, cams, n, C.byref(opts), C.c_void_p(ptr)), "hmrt_trace_host")
         return out_host
+
+    def trace_host_begin(self, W: int, H: int, cameras, opts: TraceOpts, out_host):
+        """hmrt_trace_host_begin: enqueue a host-output call and return; out_host (pinned) must stay valid and untouched until the
+        matching trace_host_wait().  Up to two calls may be in flight (double-buffered renderer)."""
+        cams = _cam_array(cameras)
+        n = len(cams)
+        ptr = self._host_ptr(out_host, n * rows_local(H, opts.tile_first, opts.tile_stride) * W * 3)
+        self._bind_stream()
+        check(self.lib.hmrt_trace_host_begin(self._h, W, H, cams, n, C.byref(opts), C.c_void_p(ptr)), "hmrt_trace_host_begin")
+
+    def trace_host_wait(self):
+        """hmrt_trace_host_wait: the oldest call begun and not yet waited for has delivered all its frames."""
+        check(self.lib.hmrt_trace_host_wait(self._h), "hmrt_trace_host_wait")
 
     def copy_tiles_to_frames(self, tiles, frames, W: int, H: int, n_frames: int, tile_first: int, tile_stride: int):
         """Compact row-tile output of a sharded trace -> its place in whole frames (possibly peer memory), 2-D device copies."""

@@ -161,6 +161,17 @@ int hmrt_trace(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_
 int hmrt_trace_host(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
                     const hmrt_trace_opts* opts, uint8_t* h_rgb);
 
+/* The same call in two halves, for a double-buffered renderer: _begin returns once the work is enqueued (the cameras have
+ * been consumed; h_rgb must stay valid and untouched), _wait returns when the OLDEST call begun and not yet waited for has
+ * delivered all its frames.  Up to HMRT_MAX_HOST_CALLS_IN_FLIGHT calls may be in flight, each rendering into its own
+ * context-owned device framebuffer: the traversal of call k + 1 runs under the device->host copies of call k (the
+ * reference serialises trace and read-back every frame, main.cpp:947-966).  HMRT_E_STATE: _begin with the maximum already
+ * in flight, _wait with nothing in flight.  hmrt_trace_host == _begin + collect everything. */
+#define HMRT_MAX_HOST_CALLS_IN_FLIGHT 2
+int hmrt_trace_host_begin(hmrt_ctx* ctx, int W, int H, const hmrt_camera* h_cameras, int n_frames,
+                          const hmrt_trace_opts* opts, uint8_t* h_rgb);
+int hmrt_trace_host_wait(hmrt_ctx* ctx);
+
 /* Number of local rows selected by (H, tile_first, tile_stride). */
 int hmrt_rows_local(int H, int tile_first, int tile_stride);
 

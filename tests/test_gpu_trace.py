@@ -157,6 +157,46 @@ def test_trace_host_large_frames_split_last_launch(cuda_ctx, host_variant, W, H,
         assert (host.numpy() == dev).all()
 
 
+def test_trace_host_begin_wait_two_calls_in_flight(cuda_ctx, host_variant):
+    """hmrt_trace_host_begin / _wait: two calls in flight into two host buffers (different cameras, different sizes) deliver what
+    the synchronous call delivers; the state errors; a synchronous call collects calls still in flight."""
+    import gpulib
+    import hmrt
+
+    sc = ol.scene("r1024_l8", seed=5)
+    keep = gpulib.upload_scene(cuda_ctx, sc)  # noqa: F841
+    opts = ol.make_opts(sc["max_height"], shadows=True)
+    W, H = 1920, 1083
+    batches = [ol.cameras_for(sc, 1), ol.cameras_for(sc, 3), ol.cameras_for(sc, 5)[2:], ol.cameras_for(sc, 4)[1:]]  # the second call grows the framebuffers
+    want = [gpulib.gpu_trace(cuda_ctx, W, H, cams, opts, hits=False)[0] for cams in batches]
+    with pytest.raises(hmrt.HmrtError) as e:
+        cuda_ctx.trace_host_wait()
+    assert e.value.code == -2  # nothing in flight
+    hosts = [torch.full(w.shape, 99, dtype=torch.uint8).pin_memory() for w in want]
+    for rounds in range(2):
+        for h in hosts:
+            h.fill_(99)
+        cuda_ctx.trace_host_begin(W, H, batches[0], opts, hosts[0])
+        for k in range(1, len(batches)):
+            cuda_ctx.trace_host_begin(W, H, batches[k], opts, hosts[k])
+            if k == 1:
+                with pytest.raises(hmrt.HmrtError) as e:
+                    cuda_ctx.trace_host_begin(W, H, batches[k], opts, hosts[k])
+                assert e.value.code == -2  # two already in flight
+            cuda_ctx.trace_host_wait()
+            assert (hosts[k - 1].numpy() == want[k - 1]).all(), (rounds, k)
+        cuda_ctx.trace_host_wait()
+        assert (hosts[-1].numpy() == want[-1]).all()
+    # a synchronous call while one is in flight: both are complete when it returns
+    hosts[0].fill_(1)
+    hosts[1].fill_(1)
+    cuda_ctx.trace_host_begin(W, H, batches[0], opts, hosts[0])
+    cuda_ctx.trace_host(W, H, batches[1], opts, hosts[1])
+    assert (hosts[0].numpy() == want[0]).all() and (hosts[1].numpy() == want[1]).all()
+    with pytest.raises(hmrt.HmrtError):
+        cuda_ctx.trace_host_wait()
+
+
 def test_many_frames_in_one_call_equal_single_frame_calls(cuda_ctx, host_variant):
     """More frames than fit in the kernel parameters (48) travel through the device-side frame table; device and host
     output of a 70-frame call must equal 70 single-frame calls."""
