@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--points", type=int, default=500_000_000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--modes", default="peer,single,direct")
-    ap.add_argument("--variants", default="", help="bin_threads:bin_per:apply_slices[:1 = generic bin kernel],... (development knobs; peer mode only)")
+    ap.add_argument("--variants", default="", help="records per thread and step of the bin pass to time (development knob): 8,4,2 (peer mode only)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ctx = hmrt.Context(0)
@@ -48,9 +48,7 @@ def main():
         rp.close()
     ctx.set_scatter_mode(0)
     for v in [v for v in args.variants.split(",") if v]:
-        th, per, sl, generic = ([int(x) for x in v.split(":")] + [0])[:4]
-        for key, val in ((0, th), (1, per), (3, generic)):
-            assert ctx.lib.hmrt_debug_raster_knob(key, val) == 0
+        assert ctx.lib.hmrt_debug_raster_knob(1, int(v)) == 0
         rp = hd.RasterPipeline(ctx, rpl.COARSE, rpl.LEVELS, single=True, force_mode="peer")
         best = None
         for _ in range(args.reps):
@@ -60,8 +58,7 @@ def main():
         out["variant_" + v] = {**best, "total_ms": sum(best.values())}
         hashes["variant_" + v] = rpl.finest_hash(torch, pyr[idx[0]:])
         rp.close()
-    for key in (0, 1, 3):
-        ctx.lib.hmrt_debug_raster_knob(key, 0)
+    ctx.lib.hmrt_debug_raster_knob(1, 0)
     out["hashes_equal"] = len(set(hashes.values())) == 1
     print(json.dumps(out))
 

@@ -9,11 +9,11 @@
  *
  *   pass 1  rx_bin_kernel     streams the records through shared memory with TMA bulk copies (cp.async.bulk + mbarrier,
  *                             two stages: chunk k+1 is in flight while chunk k is decoded), decodes each point once,
- *                             counting-sorts the chunk's (cell, height bits) pairs by grid tile (16 x 16 tiles) in shared
- *                             memory and appends every tile's run to the CTA's private slice of that tile's bucket:
- *                             no global atomics, lanes store to a few contiguous runs.
- *   pass 2  rx_apply_kernel   walks the buckets tile by tile, so the part of the grid under a tile (4 MB at 16384^2) stays
- *                             L2-resident while its RED.MAXes land.
+ *                             counting-sorts the chunk's (cell, height bits) pairs by grid tile (2048^2 cells: 8 x 8 tiles at
+ *                             16384^2) in shared memory and appends every tile's run to the CTA's private slice of that
+ *                             tile's bucket: no global atomics, lanes store to a few contiguous runs.
+ *   pass 2  rx_apply_kernel   walks the buckets tile by tile, so the part of the grid under a tile (16 MB) stays L2-resident
+ *                             while its RED.MAXes land.
  *
  * Multi-GPU (BASELINE config 4: points sharded by contiguous range).  The north star's exchange is a max all-reduce of the
  * dense finest level (1 GiB per rank at 16384^2, 93 % of it untouched by a rank's own points).  Because pass 1 already
@@ -36,9 +36,8 @@
 
 namespace hmrt {
 
-constexpr int kBinThreads = 256; /* CTA size of the apply pass; the bin pass is instantiated for 256 and 512 threads */
+constexpr int kBinThreads = 256; /* CTA size of the apply pass */
 constexpr int kMaxTiles = 256; /* binned_tile_shift() gives at most 16 x 16 tiles (usually 8 x 8) */
-constexpr int kMaxPer = 8;     /* records per thread and step */
 constexpr int kMaxPeers = 16;
 constexpr size_t kHeaderBytes = 4096;
 
@@ -70,7 +69,7 @@ struct BinParams {
   const uint8_t* records;
   int64_t n;
   int record_len;
-  int per;                /* records per thread and step: chunk = kBinThreads * per */
+  int per;                /* records per thread and step: chunk = kBinCtaThreads * per (a template parameter of the kernel launched) */
   void* pairs;            /* [n_tiles][n_slices][slice_cap] (cell, height bits) pairs, or -- with colour keys -- (cell, height
                            * bits, key lo, key hi) quads */
   uint32_t* counts;       /* [n_tiles][n_slices] */
@@ -119,212 +118,29 @@ __device__ __forceinline__ void apply_pair(int* finest, unsigned long long* keys
 }
 
 /*
- * Pass 1.  Shared memory: [2 mbarriers][fill, hist, offs, dest0: 4 x 256 u32][sdest: chunk u32][spair: chunk uint2]
- * [stage 0][stage 1], a stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
+ * Pass 1.  256 threads x PER records per step (PER = 8 -> steps of 2048 points; 4 or 2 when the records are so long that two
+ * CTAs would no longer fit an SM), two stages of TMA bulk copies.  The record layout (ALIGNED: 20 / 28-byte records whose
+ * words are aligned; else five words and funnel shifts), the cell-size form (POW2: the reference's 2.0 -> one multiplication;
+ * else the IEEE division) and the step size are compile-time facts, so the decodes of a thread are one straight-line block,
+ * run as three passes over its records -- loads, arithmetic, ranks -- whose latencies overlap.  The step:
+ *   A  decode; rank of every point inside its tile = value returned by a shared-memory atomicAdd on the tile's counter
+ *   B  one thread per tile: its warp derives the base of its group of 32 tiles itself (sum of the earlier groups' counts,
+ *      butterfly) and scans its own 32 counts -- no single-warp prefix while the others wait; slice bookkeeping
+ *   C  the pairs go to their sorted place in shared memory
+ *   D  write-out: consecutive lanes hit consecutive addresses inside a tile's run
+ * with three CTA barriers (the histogram is double buffered and cleared in B; what D reads is next written behind two
+ * barriers of the following step).  Every shared-memory access is an LDS / STS on a compile-time offset of the dynamic window.
+ * Shared memory: [2 mbarriers][fill 256][hist 2 x 256][offs, dest0 256 x 2][sdest chunk][spair chunk][stage 0][stage 1], a
+ * stage = chunk * record_len bytes (+ 16 so that the 5-word head load of the last record stays inside).
  */
-template <int THREADS, bool KEYS>
-__global__ void __launch_bounds__(THREADS) rx_bin_kernel(const __grid_constant__ BinParams p) {
-  typedef typename PairOf<KEYS>::type Pair;
-  extern __shared__ __align__(128) uint8_t rx_smem[];
-  const int chunk = THREADS * p.per;
-  uint32_t* fill = reinterpret_cast<uint32_t*>(rx_smem + 16); /* entries used in this CTA's slice of each bucket (persistent) */
-  uint32_t* hist = fill + kMaxTiles;                          /* points of this step per tile */
-  uint32_t* offs = hist + kMaxTiles;                          /* exclusive prefix of hist */
-  uint32_t* dest0 = offs + kMaxTiles;                         /* first destination index of this step's run, or ~0u: slice full */
-  uint32_t* sdest = dest0 + kMaxTiles;                        /* [chunk] destination pair index per sorted slot */
-  Pair* spair = reinterpret_cast<Pair*>((reinterpret_cast<uintptr_t>(sdest + chunk) + 15) & ~(uintptr_t)15); /* [chunk] sorted pairs */
-  const uint32_t stage_bytes = ((uint32_t)chunk * (uint32_t)p.record_len + 16u + 127u) & ~127u;
-  uint8_t* stage0 = reinterpret_cast<uint8_t*>(spair + chunk);
-  stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(rx_smem);
-  const uint32_t stage0_s = (uint32_t)__cvta_generic_to_shared(stage0);
-  __shared__ uint32_t total_s;
-
-  const uint32_t n_slices = gridDim.x;
-  for (int t = threadIdx.x; t < kMaxTiles; t += THREADS) {
-    fill[t] = (p.accumulate && t < p.n_tiles) ? p.counts[(size_t)t * n_slices + blockIdx.x] : 0u;
-    hist[t] = 0;
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int64_t n_chunks = (p.n + chunk - 1) / chunk;
-  /* issue the load of chunk c into stage s (thread 0 issues the bulk copy, the < 16 tail bytes of the very last chunk
-   * are copied by the first lanes; every use is separated from this point by at least one __syncthreads) */
-  auto issue = [&](int64_t c, int s) {
-    const int64_t first = c * chunk;
-    const int64_t remaining = p.n - first;
-    const uint32_t count = remaining < chunk ? (uint32_t)remaining : (uint32_t)chunk;
-    const uint32_t bytes = count * (uint32_t)p.record_len, bulk = bytes & ~15u;
-    const uint8_t* src = p.records + first * p.record_len; /* 16-byte aligned: chunk * record_len % 16 == 0 */
-    if (threadIdx.x == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the stage before the async write */
-      if (bulk) {
-        mbar_expect_tx(bar0 + 8 * s, bulk);
-        tma_load_1d(stage0_s + (uint32_t)s * stage_bytes, src, bulk, bar0 + 8 * s);
-      } else {
-        mbar_arrive(bar0 + 8 * s);
-      }
-    }
-    if (threadIdx.x < bytes - bulk) stage0[(size_t)s * stage_bytes + bulk + threadIdx.x] = __ldg(src + bulk + threadIdx.x);
-  };
-
-  int64_t c = (blockIdx.x + gridDim.x - p.cta_rot % gridDim.x) % gridDim.x; /* slices stay indexed by blockIdx.x */
-  if (c < n_chunks) issue(c, 0);
-  __syncthreads();
-  for (int k = 0; c < n_chunks; ++k, c += gridDim.x) {
-    const int s = k & 1;
-    if (c + gridDim.x < n_chunks) issue(c + gridDim.x, s ^ 1);
-    mbar_wait(bar0 + 8 * s, (uint32_t)(k >> 1) & 1u);
-    const uint32_t stage_s = stage0_s + (uint32_t)s * stage_bytes;
-    const int64_t remaining = p.n - c * chunk;
-    const int count = remaining < chunk ? (int)remaining : chunk;
-
-    /* A: decode, rank inside the tile.  Same arithmetic as point_to_cell (main.cpp:200-209), with the conversions taken off
-     * the XU pipe: (double)int32 by the 2^52 + 2^31 bias trick (exact), and -- since floor(t) >= 0 <=> t >= 0 and
-     * floor(t) < res0 <=> t < res0 for an integer res0 -- the range test on t itself and floor(t) read off the significand of
-     * t + 2^23 rounded toward -inf (0 <= t < 2^23). */
-    uint32_t cell[kMaxPer], hb[kMaxPer], slot[kMaxPer], rgb[KEYS ? kMaxPer : 1];
-    const float r0f = (float)p.sp.res0;
-    const bool aligned4 = (p.record_len & 3) == 0;
-#pragma unroll
-    for (int q = 0; q < kMaxPer; ++q) {
-      slot[q] = 0xffffffffu;
-      const int i = q * THREADS + threadIdx.x;
-      if (q < p.per && i < count) {
-        const uint32_t ra = stage_s + (uint32_t)i * (uint32_t)p.record_len;
-        RecordHead rh;
-        if (aligned4) { /* 20 / 28-byte records: X, Y, Z and the flags word are aligned words */
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
-          asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(ra));
-          asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(ra));
-          asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(ra));
-          rh.x = (int32_t)w0, rh.y = (int32_t)w1, rh.z = (int32_t)w2, rh.tail = w3;
-        } else {
-          rh = load_record_head_shared(ra);
-        }
-        /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double */
-        const double bias = 4503601774854144.0; /* 2^52 + 2^31 */
-        const double rx_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.x ^ 0x80000000u)), bias);
-        const double ry_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.y ^ 0x80000000u)), bias);
-        const double rz_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)rh.z ^ 0x80000000u)), bias);
-        const double gx = __dadd_rn(__dmul_rn(rx_, p.sp.scale[0]), p.sp.offset[0]);
-        const double gy = __dadd_rn(__dmul_rn(ry_, p.sp.scale[1]), p.sp.offset[1]);
-        const double gz = __dadd_rn(__dmul_rn(rz_, p.sp.scale[2]), p.sp.offset[2]);
-        const float fX = div_cell(__double2float_rn(__dsub_rn(gx, p.sp.mn[0])), p.sp.cell[0], p.sp.rcell[0]); /* :200 */
-        const float fY = div_cell(__double2float_rn(__dsub_rn(gy, p.sp.mn[1])), p.sp.cell[1], p.sp.rcell[1]); /* :201 */
-        const float fZ = div_cell(__double2float_rn(__dsub_rn(gz, p.sp.mn[2])), p.sp.cell[2], p.sp.rcell[2]); /* :202 */
-        const float tx = __fsub_rn(fX, p.sp.origin[0]), ty = __fsub_rn(fY, p.sp.origin[1]);                   /* :205-206 */
-        const bool inside = tx >= 0.0f && tx < r0f && ty >= 0.0f && ty < r0f;                                 /* :209 */
-        /* the colour is written before the height test (main.cpp:223-224 precede :229): with keys, points below the floor
-         * still travel, carrying +0.0f (a no-op for the height) */
-        if (inside && ((rh.tail >> 24) & 0x1fu) != 7u && (KEYS || fZ >= 0.0f)) {
-          const uint32_t cx = __float_as_uint(__fadd_rd(tx, 8388608.0f)) & 0x7fffffu;
-          const uint32_t cy = __float_as_uint(__fadd_rd(ty, 8388608.0f)) & 0x7fffffu;
-          cell[q] = cx + cy * (uint32_t)p.sp.res0;
-          hb[q] = fZ >= 0.0f ? __float_as_uint(fZ) : 0u;
-          if (KEYS) {
-            rgb[q] = 0;
-            if (p.sp.rgb_off >= 0) { /* three u16, 2-byte aligned in every LAS 1.2 format */
-              uint32_t r16, g16, b16;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r16) : "r"(ra + (uint32_t)p.sp.rgb_off));
-              asm volatile("ld.shared.u16 %0, [%1+2];" : "=r"(g16) : "r"(ra + (uint32_t)p.sp.rgb_off));
-              asm volatile("ld.shared.u16 %0, [%1+4];" : "=r"(b16) : "r"(ra + (uint32_t)p.sp.rgb_off));
-              rgb[q] = (color16(r16) << 16) | (color16(g16) << 8) | color16(b16);
-            }
-          }
-          const uint32_t tile = (cy >> p.tile_shift) * (uint32_t)p.tiles_x + (cx >> p.tile_shift);
-          slot[q] = (tile << 16) | atomicAdd(&hist[tile], 1u); /* rank < chunk <= 4096 */
-        }
-      }
-    }
-    __syncthreads();
-    /* B: exclusive prefix over the tiles (warp 0), destinations, slice bookkeeping */
-    if (threadIdx.x < 32) {
-      const int per = (p.n_tiles + 31) / 32;
-      uint32_t sum = 0;
-      for (int q = 0; q < per; ++q) {
-        const int t = threadIdx.x * per + q;
-        if (t < p.n_tiles) sum += hist[t];
-      }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)threadIdx.x >= d) incl += v;
-      }
-      uint32_t run = incl - sum;
-      for (int q = 0; q < per; ++q) {
-        const int t = threadIdx.x * per + q;
-        if (t < p.n_tiles) {
-          const uint32_t h = hist[t], f = fill[t];
-          offs[t] = run;
-          run += h;
-          if (f + h <= p.slice_cap) {
-            dest0[t] = (uint32_t)(((size_t)t * n_slices + blockIdx.x) * p.slice_cap + f); /* < 2^32: checked by the launcher */
-            fill[t] = f + h;
-          } else {
-            dest0[t] = 0xffffffffu; /* slice full: this step's points of the tile take the overflow route */
-          }
-          hist[t] = 0;
-        }
-      }
-      if (threadIdx.x == 31) total_s = incl;
-    }
-    __syncthreads();
-    /* C: scatter into sorted order (shared memory) */
-#pragma unroll
-    for (int q = 0; q < kMaxPer; ++q) {
-      if (slot[q] == 0xffffffffu) continue;
-      const uint32_t tile = slot[q] >> 16, rank = slot[q] & 0xffffu;
-      const uint32_t j = offs[tile] + rank, d0 = dest0[tile];
-      store_pair(spair + j, cell[q], hb[q], KEYS ? rgb[q] : 0u, p.first_index + c * chunk + (int64_t)(q * THREADS + (int)threadIdx.x));
-      sdest[j] = d0 == 0xffffffffu ? d0 : d0 + rank;
-    }
-    __syncthreads();
-    /* D: write out; consecutive lanes hit consecutive addresses inside a tile's run */
-    const uint32_t total = total_s;
-    uint32_t dropped = 0;
-    for (uint32_t j = threadIdx.x; j < total; j += THREADS) {
-      const uint32_t d = sdest[j];
-      const Pair v = spair[j];
-      if (d != 0xffffffffu)
-        static_cast<Pair*>(p.pairs)[d] = v;
-      else if (p.finest)
-        apply_pair(p.finest, p.keys, v);
-      else
-        ++dropped;
-    }
-    if (dropped) atomicAdd(p.overflow, dropped);
-    __syncthreads();
-  }
-  for (int t = threadIdx.x; t < p.n_tiles; t += THREADS) p.counts[(size_t)t * n_slices + blockIdx.x] = fill[t];
-}
-
-/*
- * Pass 1, the instantiation that runs on the usual input: 512 threads x 4 records per step, power-of-two cell sizes (the
- * reference's 2.0) -- everything the generic kernel above tests per point is a compile-time fact here, so the four decodes
- * of a thread are one straight-line block.  Same slices, same counts, same pairs (the order inside a run may differ: max
- * does not care).  Differences in the step:
- *   - the prefix over the tiles is computed by eight warps at once (each derives the full prefix from two 16-byte loads
- *     per lane and owns one tile per lane for the slice bookkeeping) instead of by one warp while fifteen wait;
- *   - the histogram is double buffered, so clearing it needs no barrier of its own;
- *   - every shared-memory access is an LDS / STS on a compile-time offset of the dynamic window (the generic kernel's
- *     aligned-up pointers made the sorted pairs generic LD / ST).
- * Shared memory: [2 mbarriers][fill 256][hist 2 x 256][offs, dest0 256 x 2][sdest 2048][spair 2048][stage 0][stage 1].
- */
+constexpr int kBinCtaThreads = 256;
 constexpr uint32_t kFastFill = 16, kFastHist = kFastFill + 4 * kMaxTiles, kFastOffd = kFastHist + 8 * kMaxTiles, kFastSdest = kFastOffd + 8 * kMaxTiles;
 template <bool KEYS, int CHUNK> __host__ __device__ constexpr uint32_t fast_stage0() {
   return (kFastSdest + 4u * CHUNK + (uint32_t)sizeof(typename PairOf<KEYS>::type) * CHUNK + 127u) & ~127u;
 }
 
-template <bool KEYS, bool ALIGNED, bool FULL, int kFastThreads, int kFastPer>
-__device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* stage, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
+template <bool KEYS, bool ALIGNED, bool POW2, bool FULL, int kFastThreads, int kFastPer>
+__device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* stage, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
                                             uint32_t (&hb)[kFastPer], uint32_t (&slot)[kFastPer], uint32_t (&rgb)[kFastPer]) {
   const float r0f = (float)p.sp.res0;
   const double bias = 4503601774854144.0; /* 2^52 + 2^31 */
@@ -354,16 +170,20 @@ __device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* s
   bool ok[kFastPer];
 #pragma unroll
   for (int q = 0; q < kFastPer; ++q) {
-    /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double; main.cpp:200-209 as in the generic kernel */
+    /* libLAS 1.8.0 Point::GetX(): raw * scale + offset, two roundings in double, then main.cpp:200-209 with the conversions
+     * taken off the XU pipe: (double)int32 by the 2^52 + 2^31 bias trick (exact), and -- since floor(t) >= 0 <=> t >= 0 and
+     * floor(t) < res0 <=> t < res0 for an integer res0 -- the range test on t itself */
     const double rx_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)X[q] ^ 0x80000000u)), bias);
     const double ry_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)Y[q] ^ 0x80000000u)), bias);
     const double rz_ = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)Z[q] ^ 0x80000000u)), bias);
     const double gx = __dadd_rn(__dmul_rn(rx_, p.sp.scale[0]), p.sp.offset[0]);
     const double gy = __dadd_rn(__dmul_rn(ry_, p.sp.scale[1]), p.sp.offset[1]);
     const double gz = __dadd_rn(__dmul_rn(rz_, p.sp.scale[2]), p.sp.offset[2]);
-    const float fX = __fmul_rn(__double2float_rn(__dsub_rn(gx, p.sp.mn[0])), p.sp.rcell[0]); /* :200, x / 2^k == x * 2^-k */
-    const float fY = __fmul_rn(__double2float_rn(__dsub_rn(gy, p.sp.mn[1])), p.sp.rcell[1]); /* :201 */
-    const float fZ = __fmul_rn(__double2float_rn(__dsub_rn(gz, p.sp.mn[2])), p.sp.rcell[2]); /* :202 */
+    const float vx = __double2float_rn(__dsub_rn(gx, p.sp.mn[0])), vy = __double2float_rn(__dsub_rn(gy, p.sp.mn[1]));
+    const float vz = __double2float_rn(__dsub_rn(gz, p.sp.mn[2]));
+    const float fX = POW2 ? __fmul_rn(vx, p.sp.rcell[0]) : div_cell(vx, p.sp.cell[0], p.sp.rcell[0]); /* :200, x / 2^k == x * 2^-k */
+    const float fY = POW2 ? __fmul_rn(vy, p.sp.rcell[1]) : div_cell(vy, p.sp.cell[1], p.sp.rcell[1]); /* :201 */
+    const float fZ = POW2 ? __fmul_rn(vz, p.sp.rcell[2]) : div_cell(vz, p.sp.cell[2], p.sp.rcell[2]); /* :202 */
     const float tx = __fsub_rn(fX, p.sp.origin[0]), ty = __fsub_rn(fY, p.sp.origin[1]);      /* :205-206 */
     const bool inside = tx >= 0.0f && tx < r0f && ty >= 0.0f && ty < r0f;                    /* :209 */
     /* the colour is written before the height test (main.cpp:223-224 precede :229): with keys, points below the floor still
@@ -392,9 +212,10 @@ __device__ __forceinline__ void fast_decode(const BinParams& p, const uint8_t* s
   }
 }
 
-template <bool KEYS, bool ALIGNED, int kFastThreads, int kFastPer, int MIN_CTAS>
-__global__ void __launch_bounds__(kFastThreads, MIN_CTAS) rx_bin_fast_kernel(const __grid_constant__ BinParams p) {
+template <bool KEYS, bool ALIGNED, bool POW2, int kFastPer>
+__global__ void __launch_bounds__(kBinCtaThreads, 2) rx_bin_kernel(const __grid_constant__ BinParams p) {
   typedef typename PairOf<KEYS>::type Pair;
+  constexpr int kFastThreads = kBinCtaThreads;
   constexpr int kFastChunk = kFastThreads * kFastPer;
   constexpr uint32_t kFastSpair = kFastSdest + 4 * kFastChunk;
   static_assert(kFastThreads >= kMaxTiles, "phase B: one thread per tile");
@@ -425,7 +246,9 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) rx_bin_fast_kernel(con
 
   const int64_t n_chunks = (p.n + kFastChunk - 1) / kFastChunk;
   const int tiles_padded = (p.n_tiles + 31) & ~31; /* whole warps of phase B */
-  auto issue = [&](int64_t c, int s) { /* as in the generic kernel */
+  /* issue the load of chunk c into stage s (thread 0 issues the bulk copy, the < 16 tail bytes of the very last chunk are
+   * copied by the first lanes; every use is separated from this point by at least one __syncthreads) */
+  auto issue = [&](int64_t c, int s) {
     const int64_t first = c * kFastChunk;
     const int64_t remaining = p.n - first;
     const uint32_t count = remaining < kFastChunk ? (uint32_t)remaining : (uint32_t)kFastChunk;
@@ -458,9 +281,9 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) rx_bin_fast_kernel(con
     /* A: decode, rank inside the tile */
     uint32_t cell[kFastPer], hb[kFastPer], slot[kFastPer], rgb[kFastPer];
     if (count == kFastChunk)
-      fast_decode<KEYS, ALIGNED, true, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
+      bin_decode<KEYS, ALIGNED, POW2, true, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
     else
-      fast_decode<KEYS, ALIGNED, false, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
+      bin_decode<KEYS, ALIGNED, POW2, false, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
     __syncthreads();
     /* B: thread t of the first eight warps owns tile t.  Its warp sums, lane by lane, the counts of the tiles of all earlier
      * groups of 32 (a butterfly turns that into the group's base) and scans its own 32 counts: no second barrier, no
@@ -656,51 +479,39 @@ struct BinGeometry {
 };
 
 /* development knobs (benchmarks/raster_probe.py); 0 = the built-in choice */
-static int g_knob_bin_threads = 0, g_knob_bin_per = 0, g_knob_bin_generic = 0;
+static int g_knob_bin_per = 0;
+
+template <int PER>
+static const void* bin_kernel_of(bool keys, bool aligned, bool pow2) {
+#define HMRT_BIN_K(K, A, P) reinterpret_cast<const void*>(&rx_bin_kernel<K, A, P, PER>)
+  return keys ? (aligned ? (pow2 ? HMRT_BIN_K(true, true, true) : HMRT_BIN_K(true, true, false))
+                         : (pow2 ? HMRT_BIN_K(true, false, true) : HMRT_BIN_K(true, false, false)))
+              : (aligned ? (pow2 ? HMRT_BIN_K(false, true, true) : HMRT_BIN_K(false, true, false))
+                         : (pow2 ? HMRT_BIN_K(false, false, true) : HMRT_BIN_K(false, false, false)));
+#undef HMRT_BIN_K
+}
 
 static int bin_geometry(int record_len, bool keys, const ScatterParams& sp, BinGeometry& g) {
-  /* The specialised kernel: 256 threads x 8 records = steps of 2048 points, two CTAs per SM (measured best of 512 x 4, 512 x 2,
-   * 256 x 4, 256 x 8: 2.69 / 3.25 / 2.98 / 2.58 ms for 500 M points, profiles/raw_r02/raster_bin_step_geometry.json); records so
-   * long that two CTAs no longer fit take 256 x 4.  Anything else (a cell size that is not a power of two, the development
-   * knobs) runs the generic kernel. */
-  const bool fast_ok = !g_knob_bin_generic && !g_knob_bin_threads && !g_knob_bin_per && sp.rcell[0] != 0.0f && sp.rcell[1] != 0.0f && sp.rcell[2] != 0.0f;
+  /* 256 threads x 8 records = steps of 2048 points, two CTAs per SM: measured best of 512 x 4, 512 x 2, 256 x 4, 256 x 8 (2.69 /
+   * 3.25 / 2.98 / 2.58 ms for 500 M points, profiles/raw_r02/raster_bin_step_geometry.json).  Longer records take the largest
+   * step with which two CTAs still fit an SM (record_len <= 64: 256 x 2 always does). */
   const bool aligned = (record_len & 3) == 0;
-  if (fast_ok) {
-#define HMRT_FAST_CASE(T, P, M)                                                                                                          \
-  {                                                                                                                                      \
-    const size_t smem = (keys ? fast_stage0<true, T * P>() : fast_stage0<false, T * P>()) + 2 * (((size_t)T * P * record_len + 16 + 127) & ~(size_t)127); \
-    if (smem <= 112 * 1024) {                                                                                                            \
-      g.fn = keys ? (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, true, T, P, M>)                                   \
-                             : reinterpret_cast<const void*>(&rx_bin_fast_kernel<true, false, T, P, M>))                                 \
-                  : (aligned ? reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, true, T, P, M>)                                  \
-                             : reinterpret_cast<const void*>(&rx_bin_fast_kernel<false, false, T, P, M>));                               \
-      g.threads = T, g.per = P, g.chunk = T * P, g.smem = smem;                                                                          \
-      HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));                                   \
-      HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));                                 \
-      if (g.ctas_per_sm >= 2) return 0;                                                                                                  \
-    }                                                                                                                                    \
+  const bool pow2 = sp.rcell[0] != 0.0f && sp.rcell[1] != 0.0f && sp.rcell[2] != 0.0f;
+  g.threads = kBinCtaThreads;
+  for (int per = g_knob_bin_per ? g_knob_bin_per : 8; per >= 2; per >>= 1) {
+    const int chunk = kBinCtaThreads * per;
+    const size_t stage = ((size_t)chunk * record_len + 16 + 127) & ~(size_t)127;
+    g.per = per, g.chunk = chunk;
+    g.fn = per == 8 ? bin_kernel_of<8>(keys, aligned, pow2) : per == 4 ? bin_kernel_of<4>(keys, aligned, pow2) : bin_kernel_of<2>(keys, aligned, pow2);
+    g.smem = (per == 8 ? (keys ? fast_stage0<true, 2048>() : fast_stage0<false, 2048>())
+              : per == 4 ? (keys ? fast_stage0<true, 1024>() : fast_stage0<false, 1024>())
+                         : (keys ? fast_stage0<true, 512>() : fast_stage0<false, 512>())) + 2 * stage;
+    if (g.smem > 220 * 1024) continue;
+    HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));
+    if (g.ctas_per_sm >= 2 || (per == 2 && g.ctas_per_sm >= 1)) return 0;
   }
-    HMRT_FAST_CASE(256, 8, 2)
-    HMRT_FAST_CASE(256, 4, 2)
-#undef HMRT_FAST_CASE
-  }
-  g.threads = g_knob_bin_threads ? g_knob_bin_threads : 512;
-  g.per = g_knob_bin_per ? g_knob_bin_per : 4;
-  if (g.threads * g.per > 4096) g.per = 4096 / g.threads;
-  g.fn = keys ? (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, true>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, true>))
-              : (g.threads == 512 ? reinterpret_cast<const void*>(&rx_bin_kernel<512, false>) : reinterpret_cast<const void*>(&rx_bin_kernel<256, false>));
-  for (;;) {
-    g.chunk = g.threads * g.per;
-    const size_t stage = ((size_t)g.chunk * record_len + 16 + 127) & ~(size_t)127;
-    g.smem = 16 + 4 * kMaxTiles * sizeof(uint32_t) + (size_t)g.chunk * (sizeof(uint32_t) + (keys ? sizeof(uint4) : sizeof(uint2))) + 16 + 128 + 2 * stage;
-    if (g.smem <= 220 * 1024 || g.per == 1) break;
-    g.per >>= 1; /* long records: smaller steps */
-  }
-  if (g.smem > 220 * 1024) return HMRT_E_ARG;
-  HMRT_CUDA(cudaFuncSetAttribute(g.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-  HMRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.ctas_per_sm, g.fn, g.threads, g.smem));
-  if (g.ctas_per_sm < 1) return HMRT_E_ARG;
-  return 0;
+  return HMRT_E_ARG;
 }
 
 static int launch_bin(const BinGeometry& g, const BinParams& bp, unsigned grid, cudaStream_t stream) {
@@ -814,13 +625,10 @@ extern "C" {
 
 int hmrt_rx_barrier(hmrt_rx* rx);
 
-/* Development knobs of the binned rasterisation (not part of include/hmrt.h): key 0 = CTA size of the bin pass (256 / 512),
- * 1 = records per thread and step (either one selects the generic bin kernel), 3 = 1: the generic bin kernel; value 0 restores the
- * built-in choice. */
+/* Development knob of the binned rasterisation (not part of include/hmrt.h): key 1 = records per thread and step of the bin
+ * pass (8, 4 or 2; 0 restores the built-in choice). */
 int hmrt_debug_raster_knob(int key, int value) {
-  if (key == 0 && (value == 0 || value == 256 || value == 512)) hmrt::g_knob_bin_threads = value;
-  else if (key == 1 && value >= 0 && value <= 8) hmrt::g_knob_bin_per = value;
-  else if (key == 3 && value >= 0 && value <= 1) hmrt::g_knob_bin_generic = value;
+  if (key == 1 && (value == 0 || value == 2 || value == 4 || value == 8)) hmrt::g_knob_bin_per = value;
   else return HMRT_E_ARG;
   return 0;
 }
