@@ -48,9 +48,10 @@ def _rx_rasterise(ctx, hdr, rec, coarse, levels, cell=(2.0, 2.0, 2.0), origin=(0
         lib.hmrt_rx_destroy(rx)
 
 
-@pytest.mark.parametrize("fmt,record_len,pieces", [(0, None, 1), (2, None, 1), (1, 28, 3), (3, 34, 2), (0, 32, 1), (2, 48, 1)])
+@pytest.mark.parametrize("fmt,record_len,pieces", [(0, None, 1), (2, None, 1), (1, 28, 3), (3, 34, 2), (0, 32, 1), (2, 48, 1), (1, 64, 2), (3, 62, 1)])
 def test_rx_world1_bit_exact(cuda_ctx, fmt, record_len, pieces):
-    """20-byte records take 8 records per thread and step, longer ones 4; several hmrt_rx_bin calls continue the slices."""
+    """20 / 26 / 28-byte records take 8 records per thread and step, 32..48-byte ones 4, the longest (up to 64 bytes) 2; aligned and
+    2-mod-4 record lengths; several hmrt_rx_bin calls continue the slices."""
     r0, levels = 2048, 8
     coarse = r0 >> (levels - 1)
     n = 700_001 if pieces == 1 else 300_007  # not a multiple of the step size: exercises the partial last chunk and its tail bytes
