@@ -31,12 +31,32 @@ COARSE = R0 >> (LEVELS - 1)
 
 def make_records(n, fmt, seed, order):
     """n LAS records (format 0: 20 B, format 2: 26 B) on the device; 'random' = uniformly scattered points,
-    'swath' = points sorted by scan line (row-major cell order with jitter), like an airborne survey file."""
+    'swath' = points sorted by scan line (row-major cell order with jitter), 'scanline' = pulses along zig-zag scan lines with
+    1-3 returns each, consecutive in the file: the acquisition order of an airborne survey."""
     rec_len = las.RECORD_MIN_LEN[fmt]
     g = torch.Generator(device="cuda").manual_seed(seed)
     ext_raw = int(R0 * 2.0 / 0.01)
-    X = torch.randint(0, ext_raw, (n,), device="cuda", generator=g, dtype=torch.int32)
-    if order == "swath":
+    if order == "scanline":
+        # an airborne scanner: pulses along zig-zag scan lines, 1-3 returns per pulse (13 pulses = 20 records, 1.54 per pulse) at
+        # almost the same x/y, consecutive in the file; lines and pulses spaced so that the n points cover the whole grid
+        pattern = torch.tensor([0, 1, 2, 2, 3, 4, 4, 4, 5, 6, 7, 7, 8, 9, 10, 10, 10, 11, 11, 12], device="cuda", dtype=torch.int64)
+        i = torch.arange(n, device="cuda", dtype=torch.int64)
+        pulse = (i // 20) * 13 + pattern[i % 20]
+        n_pulses = int(pulse[-1].item()) + 1
+        per_line = max(1, int(n_pulses ** 0.5))
+        line, pos = pulse // per_line, pulse % per_line
+        pos = torch.where(line % 2 == 0, pos, per_line - 1 - pos)
+        n_lines = (n_pulses + per_line - 1) // per_line
+        jx = torch.randint(-15, 16, (n,), device="cuda", generator=g, dtype=torch.int64)  # +-0.15 m between the returns of a pulse
+        jy = torch.randint(-15, 16, (n,), device="cuda", generator=g, dtype=torch.int64)
+        X = ((pos.double() + 0.5) * (ext_raw / per_line)).to(torch.int64).add_(jx).clamp_(0, ext_raw - 1).to(torch.int32)
+        Y = ((line.double() + 0.5) * (ext_raw / n_lines)).to(torch.int64).add_(jy).clamp_(0, ext_raw - 1).to(torch.int32)
+        del i, pulse, line, pos, jx, jy
+    else:
+        X = torch.randint(0, ext_raw, (n,), device="cuda", generator=g, dtype=torch.int32)
+    if order == "scanline":
+        pass
+    elif order == "swath":
         Y = (torch.arange(n, device="cuda", dtype=torch.float64) * (ext_raw / n)).to(torch.int32)
     else:
         Y = torch.randint(0, ext_raw, (n,), device="cuda", generator=g, dtype=torch.int32)
@@ -54,7 +74,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=500_000_000)
     ap.add_argument("--format", type=int, default=0, choices=[0, 2])
-    ap.add_argument("--order", default="random", choices=["random", "swath"])
+    ap.add_argument("--order", default="random", choices=["random", "swath", "scanline"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 direct atomics, 2 tile-binned")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="points of the CPU baseline sample (0 = skip)")
