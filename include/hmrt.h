@@ -202,7 +202,7 @@ int hmrt_scatter_las(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, int rec
 
 /* Rasterisation strategy of hmrt_scatter_las: 0 (default) = decide per call from a locality probe of the
  * input, 1 = one atomic max per point straight into the grid (best for survey-ordered files and small grids),
- * 2 = bin the points by grid tile (16 x 16 tiles) first (best for unordered clouds on grids larger than L2; needs 16-byte
+ * 2 = bin the points by grid tile (tiles of up to 2048 x 2048 cells, 8 to 16 per axis) first (best for unordered clouds on grids larger than L2; needs 16-byte
  *     aligned records of at most 64 bytes, else the call takes path 1; colour keys travel with the points).
  * Results are bit-identical in every mode. */
 int hmrt_set_scatter_mode(hmrt_ctx* ctx, int mode);

@@ -75,7 +75,7 @@ def test_rx_origin_cell_size_and_levels(cuda_ctx):
 
 
 def test_non_power_of_two_grid_in_every_scatter_mode(cuda_ctx):
-    """coarse_res 21 (2688^2 cells: 11 x 11 grid tiles of 256 cells, the last ones ragged): direct, forced tile-binned and the
+    """coarse_res 21 (2688^2 cells: 6 x 6 grid tiles of 512 cells, the last ones ragged): direct, forced tile-binned and the
     exchange path agree with the oracle (the old binned path's shared-memory table grew with the tile count)."""
     r0, levels = 2688, 8
     coarse = r0 >> (levels - 1)
@@ -99,7 +99,7 @@ def test_non_power_of_two_grid_in_every_scatter_mode(cuda_ctx):
     # odd coarse resolution: level 0 starts at an odd float offset -> the exchange path declines, the host falls back
     rx = C.c_void_p()
     assert cuda_ctx.lib.hmrt_rx_create(cuda_ctx._h, coarse, levels, 0, 1, 1000, C.byref(rx)) == -3
-    # 20 x 128 = 2560 cells (10 x 10 tiles): the exchange path takes it
+    # 20 x 128 = 2560 cells (5 x 5 tiles of 512): the exchange path takes it
     hdr2, rec2 = rl.synthetic_las(700_000, 2560, point_format=0, seed=22)
     want2, _ = rl.oracle_rasterise(hdr2, rec2, 20, levels, with_colors=False)
     got, overflow, err = _rx_rasterise(cuda_ctx, hdr2, rec2, 20, levels)
