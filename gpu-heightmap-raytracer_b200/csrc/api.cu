@@ -194,6 +194,24 @@ int hmrt_debug_host_mid_groups(hmrt_ctx* ctx, int groups) {
   return 0;
 }
 
+/* Checked build (make libhmrt_checked.so, HMRT_DCHECK in hmrt_internal.cuh): 1 when this library carries the device-side bounds
+ * checks; the self-test launches a kernel whose check fails on purpose and returns the CUDA error the trap produces (the
+ * context is unusable afterwards: call it from a throw-away process).  Not part of include/hmrt.h. */
+__global__ void dcheck_selftest_kernel(int v) { HMRT_DCHECK(v == 0); }
+int hmrt_debug_checked_build(void) {
+#if defined(HMRT_CHECKED)
+  return 1;
+#else
+  return 0;
+#endif
+}
+int hmrt_debug_dcheck_selftest(hmrt_ctx* ctx) {
+  if (!ctx) return HMRT_E_ARG;
+  hmrt::DeviceGuard guard(ctx->device);
+  dcheck_selftest_kernel<<<1, 1, 0, ctx->stream>>>(1);
+  return (int)cudaStreamSynchronize(ctx->stream);
+}
+
 int hmrt_set_window_variant(hmrt_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 1) return HMRT_E_ARG;
   ctx->window_variant = variant;

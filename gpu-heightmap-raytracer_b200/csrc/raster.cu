@@ -25,6 +25,7 @@ __device__ __forceinline__ void bin_point(const ScatterParams& sp, double gx, do
   uint32_t cell;
   float fZ;
   if (!point_to_cell(sp, gx, gy, gz, cls, cell, fZ)) return;
+  HMRT_DCHECK(cell < (uint32_t)sp.res0 * (uint32_t)sp.res0);
   if (keys) /* :223-224; +1 so that key 0 means "never written" */
     atomicMax(keys + cell, ((unsigned long long)(file_index + 1) << 24) | rgb);
   /* :227-233.  Negative or NaN heights never replace the +0 floor in the reference (`buf <= fZ` is

@@ -148,6 +148,7 @@ __device__ __forceinline__ void mips_tile(const MipParams& mp, const float* __re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R0 = mp.res0;
 
+  HMRT_DCHECK(tile_x >= 0 && tile_z >= 0 && (tile_x + 1) * 128 <= R0 && (tile_z + 1) * 128 <= R0);
   float4 a[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) a[r] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(warp * 8 + r) * src_pitch + lane * 4));

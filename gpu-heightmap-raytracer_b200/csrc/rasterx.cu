@@ -140,7 +140,7 @@ template <bool KEYS, int CHUNK> __host__ __device__ constexpr uint32_t fast_stag
 }
 
 template <bool KEYS, bool ALIGNED, bool POW2, bool FULL, int kFastThreads, int kFastPer>
-__device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* stage, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
+__device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* stage, uint32_t stage_bytes, int count, uint32_t* hist, uint32_t (&cell)[kFastPer],
                                             uint32_t (&hb)[kFastPer], uint32_t (&slot)[kFastPer], uint32_t (&rgb)[kFastPer]) {
   const float r0f = (float)p.sp.res0;
   const double bias = 4503601774854144.0; /* 2^52 + 2^31 */
@@ -154,6 +154,7 @@ __device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* st
     tail[q] = 7u << 24; /* past the end of the input: rejected like a class-7 point */
     if (FULL || i < count) {
       const uint32_t off = (uint32_t)i * (uint32_t)p.record_len;
+      HMRT_DCHECK(off + 20u <= stage_bytes);
       if (ALIGNED) { /* 20 / 28-byte records: X, Y, Z and the flags word are aligned words */
         const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + off);
         X[q] = (int32_t)w[0], Y[q] = (int32_t)w[1], Z[q] = (int32_t)w[2], tail[q] = w[3];
@@ -199,6 +200,7 @@ __device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* st
       rgb[q] = 0;
       if (ok[q] && p.sp.rgb_off >= 0) { /* three u16, 2-byte aligned in every LAS 1.2 format */
         const uint32_t off = (uint32_t)(q * kFastThreads + (int)threadIdx.x) * (uint32_t)p.record_len;
+        HMRT_DCHECK(off + (uint32_t)p.sp.rgb_off + 6u <= stage_bytes);
         const uint16_t* c16 = reinterpret_cast<const uint16_t*>(stage + off + (uint32_t)p.sp.rgb_off);
         rgb[q] = (color16(c16[0]) << 16) | (color16(c16[1]) << 8) | color16(c16[2]);
       }
@@ -207,6 +209,7 @@ __device__ __forceinline__ void bin_decode(const BinParams& p, const uint8_t* st
 #pragma unroll
   for (int q = 0; q < kFastPer; ++q) {
     uint32_t rank = 0;
+    HMRT_DCHECK(!ok[q] || (tile[q] < (uint32_t)p.n_tiles && cell[q] < (uint32_t)p.sp.res0 * (uint32_t)p.sp.res0));
     if (ok[q]) rank = atomicAdd(&hist[tile[q]], 1u); /* rank < 2048 */
     slot[q] = ok[q] ? (tile[q] << 16) | rank : 0xffffffffu;
   }
@@ -281,9 +284,9 @@ __global__ void __launch_bounds__(kBinCtaThreads, 2) rx_bin_kernel(const __grid_
     /* A: decode, rank inside the tile */
     uint32_t cell[kFastPer], hb[kFastPer], slot[kFastPer], rgb[kFastPer];
     if (count == kFastChunk)
-      bin_decode<KEYS, ALIGNED, POW2, true, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
+      bin_decode<KEYS, ALIGNED, POW2, true, kFastThreads, kFastPer>(p, stage, stage_bytes, count, hist, cell, hb, slot, rgb);
     else
-      bin_decode<KEYS, ALIGNED, POW2, false, kFastThreads, kFastPer>(p, stage, count, hist, cell, hb, slot, rgb);
+      bin_decode<KEYS, ALIGNED, POW2, false, kFastThreads, kFastPer>(p, stage, stage_bytes, count, hist, cell, hb, slot, rgb);
     __syncthreads();
     /* B: thread t of the first eight warps owns tile t.  Its warp sums, lane by lane, the counts of the tiles of all earlier
      * groups of 32 (a butterfly turns that into the group's base) and scans its own 32 counts: no second barrier, no
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(kBinCtaThreads, 2) rx_bin_kernel(const __grid_
       if (slot[q] == 0xffffffffu) continue;
       const uint32_t rank = slot[q] & 0xffffu;
       const uint32_t j = od[q].x + rank;
+      HMRT_DCHECK(j < (uint32_t)kFastChunk && rank < (uint32_t)kFastChunk);
       store_pair(spair + j, cell[q], hb[q], KEYS ? rgb[q] : 0u, p.first_index + c * kFastChunk + (int64_t)(q * kFastThreads + (int)threadIdx.x));
       sdest[j] = od[q].y == 0xffffffffu ? od[q].y : od[q].y + rank;
     }
@@ -334,6 +338,9 @@ __global__ void __launch_bounds__(kBinCtaThreads, 2) rx_bin_kernel(const __grid_
     for (uint32_t j = threadIdx.x; j < total; j += kFastThreads) {
       const uint32_t d = sdest[j];
       const Pair v = spair[j];
+      HMRT_DCHECK(total <= (uint32_t)kFastChunk);
+      HMRT_DCHECK(d == 0xffffffffu || (unsigned long long)d < (unsigned long long)p.n_tiles * n_slices * p.slice_cap);
+      HMRT_DCHECK(v.x < (uint32_t)p.sp.res0 * (uint32_t)p.sp.res0);
       if (d != 0xffffffffu)
         static_cast<Pair*>(p.pairs)[d] = v;
       else if (p.finest)
@@ -360,6 +367,7 @@ struct ApplyParams {
   uint32_t pieces_per_slice; /* ceil(slice_cap / kApplyPiece) */
   int* dst;
   uint32_t cell_base;
+  uint32_t dst_cells;       /* cells behind dst (bounds checks of the checked build) */
   unsigned long long* keys; /* KEYS instantiation (single GPU): colour keys, indexed like dst */
 };
 
@@ -385,6 +393,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
   const uint32_t lo = piece * kApplyPiece;
   if (lo >= count) return;
   const uint32_t hi = min(count, lo + kApplyPiece);
+  HMRT_DCHECK(count <= p.slice_cap && tile < 256u);
   if (KEYS) { /* one 16-byte quad per point */
     const uint4* src4 = reinterpret_cast<const uint4*>(base + p.pairs_off) + ((size_t)tile * p.n_slices + s) * p.slice_cap;
     for (uint32_t i = lo + lane; i < hi; i += 32 * 4) {
@@ -396,7 +405,10 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (i + (uint32_t)k * 32 < hi) apply_pair(dst, p.keys, v[k]);
+        if (i + (uint32_t)k * 32 < hi) {
+          HMRT_DCHECK(v[k].x - p.cell_base < p.dst_cells);
+          apply_pair(dst, p.keys, v[k]);
+        }
     }
     return;
   }
@@ -413,6 +425,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (i + (uint32_t)k * 32 < q_hi) {
+        HMRT_DCHECK(v[k].x - p.cell_base < p.dst_cells && v[k].z - p.cell_base < p.dst_cells);
         atomicMax(dst + v[k].x, (int)v[k].y);
         atomicMax(dst + v[k].z, (int)v[k].w);
       }
@@ -420,6 +433,7 @@ __global__ void __launch_bounds__(kBinThreads) rx_apply_kernel(const __grid_cons
   }
   if ((hi & 1u) && lane == 0) { /* only the last piece of a slice can end on an odd count */
     const uint2 v = __ldcs(src + (hi - 1));
+    HMRT_DCHECK(v.x - p.cell_base < p.dst_cells);
     atomicMax(dst + v.x, (int)v.y);
   }
 }
@@ -588,6 +602,7 @@ int scatter_binned_single(hmrt_ctx* ctx, const uint8_t* d_records, int64_t n, in
     ap.groups_per_tile = ((uint32_t)n_slices * ap.pieces_per_slice + (kBinThreads / 32) - 1) / (kBinThreads / 32);
     ap.dst = finest;
     ap.cell_base = 0;
+    ap.dst_cells = (uint32_t)sp.res0 * (uint32_t)sp.res0;
     ap.keys = keys;
     if (keys)
       rx_apply_kernel<true><<<(unsigned)n_tiles * ap.groups_per_tile, kBinThreads, 0, ctx->stream>>>(ap);
@@ -826,6 +841,7 @@ int hmrt_rx_apply(hmrt_rx* rx) {
   ap.groups_per_tile = ((uint32_t)rx->world * (uint32_t)rx->n_slices * ap.pieces_per_slice + (hmrt::kBinThreads / 32) - 1) / (hmrt::kBinThreads / 32);
   ap.dst = reinterpret_cast<int*>(rx->region + rx->band_off);
   ap.cell_base = (uint32_t)rx->band_row0[rx->rank] * (uint32_t)rx->res0;
+  ap.dst_cells = (uint32_t)(rx->band_row0[rx->rank + 1] - rx->band_row0[rx->rank]) * (uint32_t)rx->res0;
   const unsigned grid = (unsigned)(rows_owned * rx->tiles_x) * ap.groups_per_tile;
   hmrt::rx_apply_kernel<false><<<grid, hmrt::kBinThreads, 0, rx->ctx->stream>>>(ap);
   HMRT_LAUNCHED(rx->ctx);

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) compose_window_kernel(const __grid_consta
     const uint32_t per = (res & 3u) == 0 ? 4u : 1u, row_items = res / per;
     const uint32_t y = local / row_items, x = (local - y * row_items) * per;
     const uint32_t sy = y + p.cy[l], wy = sy >= res, yy = wy ? sy - res : sy;
+    HMRT_DCHECK(y < res && yy < res && x + per <= res && p.cx[l] < res && p.cy[l] < res);
     float* dst = p.out + p.idx[l] + (size_t)y * res + x;
     const uint32_t sx = x + p.cx[l];
     if (p.vec[l]) {
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(32) compose_window_tma_kernel(const __grid_con
       const uint32_t s = k % kWinStages;
       if (lane == 0) {
         const WinJob w = win_job(p, blockIdx.x + k * gridDim.x);
+        HMRT_DCHECK(w.len_a + w.len_b <= kWinPiece && (!w.tma_ok || ((w.len_a | w.len_b) & 15u) == 0));
         ring_len[s] = w.tma_ok ? w.len_a + w.len_b : 0u;
         ring_dst[s] = w.dst;
         if (w.tma_ok) {
