@@ -28,6 +28,22 @@
 #include <string.h>
 #endif
 
+/* Device-side bounds checks of the CHECKED build (make libhmrt_checked.so: -DHMRT_CHECKED; compute-sanitizer is not available
+ * on the GPU pool): every computed index of the rasterisation, window and traversal kernels is tested before it is used; a
+ * failure prints the expression and traps, so the next CUDA call of the test fails.  The product build compiles them away. */
+#if defined(HMRT_CHECKED) && defined(__CUDACC__)
+#include <stdio.h>
+#define HMRT_DCHECK(cond)                                                                                             \
+  do {                                                                                                                \
+    if (!(cond)) {                                                                                                    \
+      printf("HMRT_DCHECK failed: %s (%s:%d) block %u thread %u\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      __trap();                                                                                                       \
+    }                                                                                                                 \
+  } while (0)
+#else
+#define HMRT_DCHECK(cond) ((void)0)
+#endif
+
 namespace hmrt {
 
 /* ---- exactly-rounded fp32 primitives (never contracted) --------------------------------- */
