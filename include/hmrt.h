@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMRT_VERSION 200 /* round 2: hmrt_trace_opts grew by full_frame_output; hmrt_rx_*, hmrt_ipc_*, hmrt_trace_stats, hmrt_get_stream added */
+#define HMRT_VERSION 201 /* 200: hmrt_trace_opts grew by full_frame_output; hmrt_rx_*, hmrt_ipc_*, hmrt_trace_stats, hmrt_get_stream added; 201: hmrt_trace_host_begin / _wait */
 #define HMRT_MAX_LEVELS 16
 
 /* argument errors (negative so they never collide with cudaError_t) */

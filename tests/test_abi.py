@@ -45,7 +45,7 @@ def test_host_only_entry_points():
     from hmrt import _abi
 
     lib = _abi.load()
-    assert lib.hmrt_version() == 200
+    assert lib.hmrt_version() == 201
     res = (C.c_int * 8)()
     idx = (C.c_int64 * 8)()
     total = C.c_int64()
